@@ -1,0 +1,693 @@
+/*
+ * clr_oracle.c -- CPU restatement of the reference's hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may link or call this file; it is the checker (and the timed CPU baseline), never the
+ * product.  PARITY UNPINNED: see oracle/__init__.py -- the arithmetic restated here lives in
+ * un-vendored Julia packages and is written from recall of their published algorithms
+ * (SURVEY.md section 8c), anchored on the VerticalCAS verdicts.
+ *
+ * Reference call sites followed (paths relative to /root/reference):
+ *   src/solve.jl:210-218      controller_forward (pre -> forward(DeepZ) -> post -> 1-D collapse)
+ *   src/solve.jl:153-166      the per-cell loop that is batched here (OpenMP over cells)
+ *   src/splitters.jl:20-28    BoxSplitter -> LazySets.split (cells enumerated dim-1-fastest)
+ *   src/problem.jl:10-58      apply(postprocessing, .) for sets and vectors
+ *   src/setops.jl:76-83       box_approximation(U0)
+ *   src/simulate.jl:98-140    per-period loop: NN per trajectory, extended state, ODE solve
+ *   ext/ClosedLoopReachabilityOrdinaryDiffEqExt.jl:28-45   Tsit5() ensemble solve
+ * Upstream algorithms restated: LazySets linear_map/_linear_map_zonotope_1D, low/high,
+ *   overapproximate(Rectification(Z), Zonotope); NeuralNetworkReachability
+ *   _overapproximate_zonotope (sigmoid/tanh); ReachabilityBase _leq/_isapprox/
+ *   remove_zero_columns; OrdinaryDiffEq v6 Tsit5 perform_step, PIController, initdt,
+ *   DiffEqBase fastpow.
+ *
+ * All matrices are column-major (Julia native).  Compile with -ffp-contract=off so that
+ * a*b+c is two roundings as in Julia.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define CLRO_MAX_LAYERS 32
+#define ZTOL (10.0 * 2.220446049250313e-16)
+#define RTOL 1.4901161193847656e-08
+
+typedef struct {
+    int n_layers;
+    int dims[CLRO_MAX_LAYERS + 1];
+    int act[CLRO_MAX_LAYERS]; /* 0 Id, 1 ReLU, 2 Sigmoid, 3 Tanh */
+    double* W[CLRO_MAX_LAYERS]; /* m x n column-major */
+    double* b[CLRO_MAX_LAYERS];
+} clro_net;
+
+typedef struct {
+    int64_t n_cells;
+    int64_t sum_p_in[CLRO_MAX_LAYERS];     /* generator columns entering layer l, summed over cells */
+    int64_t sum_unstable[CLRO_MAX_LAYERS]; /* generators appended by activation l */
+    int64_t near_threshold;                /* ReLU neurons with |l| or |u| < 1e-12 */
+    int64_t max_p_out;
+    double flops;                          /* sum_l 2 m_l n_l (p_l + 1) */
+} clro_stats;
+
+int clro_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+clro_net* clro_net_create(int n_layers, const int* dims, const int* act, const double* const* W,
+                          const double* const* b) {
+    if (n_layers < 1 || n_layers > CLRO_MAX_LAYERS) return NULL;
+    clro_net* net = (clro_net*)calloc(1, sizeof(clro_net));
+    net->n_layers = n_layers;
+    for (int l = 0; l <= n_layers; l++) net->dims[l] = dims[l];
+    for (int l = 0; l < n_layers; l++) {
+        size_t m = dims[l + 1], n = dims[l];
+        net->act[l] = act[l];
+        net->W[l] = (double*)malloc(sizeof(double) * m * n);
+        net->b[l] = (double*)malloc(sizeof(double) * m);
+        memcpy(net->W[l], W[l], sizeof(double) * m * n);
+        memcpy(net->b[l], b[l], sizeof(double) * m);
+    }
+    return net;
+}
+
+void clro_net_free(clro_net* net) {
+    if (!net) return;
+    for (int l = 0; l < net->n_layers; l++) { free(net->W[l]); free(net->b[l]); }
+    free(net);
+}
+
+/* ---- ReachabilityBase.Comparison ------------------------------------------------------ */
+static int isapproxzero(double x) { return fabs(x) <= ZTOL; }
+static int approx(double x, double y) {
+    if (isapproxzero(x) && isapproxzero(y)) return 1;
+    return x == y || fabs(x - y) <= RTOL * fmax(fabs(x), fabs(y));
+}
+static int leq(double x, double y) { return x <= y || approx(x, y); }
+
+/* ---- a zonotope with growable generator storage (column-major n x p) ------------------- */
+typedef struct { int n, p, cap; double* c; double* G; } zono;
+
+static void z_init(zono* z, int n, int cap) {
+    z->n = n; z->p = 0; z->cap = cap > 0 ? cap : 1;
+    z->c = (double*)malloc(sizeof(double) * (n > 0 ? n : 1));
+    z->G = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1) * z->cap);
+}
+static void z_free(zono* z) { free(z->c); free(z->G); }
+static void z_reserve(zono* z, int cols) {
+    if (cols <= z->cap) return;
+    int nc = z->cap * 2; if (nc < cols) nc = cols;
+    z->G = (double*)realloc(z->G, sizeof(double) * (size_t)z->n * nc);
+    z->cap = nc;
+}
+
+/* remove_zero_columns: drop generators that are exactly zero in every row */
+static void z_remove_zero_columns(zono* z) {
+    int q = 0;
+    for (int j = 0; j < z->p; j++) {
+        int nz = 0;
+        for (int i = 0; i < z->n; i++) if (z->G[(size_t)j * z->n + i] != 0.0) { nz = 1; break; }
+        if (nz) {
+            if (q != j) memcpy(z->G + (size_t)q * z->n, z->G + (size_t)j * z->n, sizeof(double) * z->n);
+            q++;
+        }
+    }
+    z->p = q;
+}
+
+/* linear_map(M, Z) + translate: Zonotope(M*c + b, M*G); one-row M yields a single generator */
+static void z_affine(const double* W, const double* b, int m, int n, const zono* in, zono* out) {
+    z_init(out, m, m == 1 ? 1 : in->p);
+    for (int i = 0; i < m; i++) {
+        double s = 0.0;
+        for (int k = 0; k < n; k++) s += W[(size_t)k * m + i] * in->c[k];
+        out->c[i] = b ? s + b[i] : s;
+    }
+    if (m == 1) {
+        double gi = 0.0;
+        for (int j = 0; j < in->p; j++) {
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s += W[k] * in->G[(size_t)j * n + k];
+            gi += fabs(s);
+        }
+        out->G[0] = gi; out->p = 1;
+        return;
+    }
+    for (int j = 0; j < in->p; j++)
+        for (int i = 0; i < m; i++) {
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s += W[(size_t)k * m + i] * in->G[(size_t)j * n + k];
+            out->G[(size_t)j * m + i] = s;
+        }
+    out->p = in->p;
+}
+
+static double sigm(double x) { return 1.0 / (1.0 + exp(-x)); }
+static double sigm_p(double x) { double ex = exp(x); return ex / ((1.0 + ex) * (1.0 + ex)); }
+static double tanh_p(double x) { double t = tanh(x); return 1.0 - t * t; }
+
+/* activation relaxation in place; returns number of appended generators */
+static int z_activation(zono* z, int act, int64_t* near_thr) {
+    if (act == 0) return 0;
+    int n = z->n, p = z->p;
+    int* rows = (int*)malloc(sizeof(int) * (n > 0 ? n : 1));
+    double* mus = (double*)malloc(sizeof(double) * (n > 0 ? n : 1));
+    int q = 0;
+    for (int i = 0; i < n; i++) {
+        double lo = z->c[i], hi = z->c[i];
+        for (int j = 0; j < p; j++) { double a = fabs(z->G[(size_t)j * n + i]); lo -= a; hi += a; }
+        if (act == 1) {
+            if (near_thr && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) (*near_thr)++;
+            if (!leq(lo, 0.0)) continue;
+            if (leq(hi, 0.0)) {
+                z->c[i] = 0.0;
+                for (int j = 0; j < p; j++) z->G[(size_t)j * n + i] = 0.0;
+            } else {
+                double lam = hi / (hi - lo);
+                double mu = -lam * lo / 2;
+                z->c[i] = z->c[i] * lam + mu;
+                for (int j = 0; j < p; j++) z->G[(size_t)j * n + i] = z->G[(size_t)j * n + i] * lam;
+                rows[q] = i; mus[q] = mu; q++;
+            }
+        } else {
+            double ly = act == 2 ? sigm(lo) : tanh(lo);
+            double uy = act == 2 ? sigm(hi) : tanh(hi);
+            if (approx(lo, hi)) {
+                z->c[i] = uy;
+                for (int j = 0; j < p; j++) z->G[(size_t)j * n + i] = 0.0;
+            } else {
+                double dl = act == 2 ? sigm_p(lo) : tanh_p(lo);
+                double du = act == 2 ? sigm_p(hi) : tanh_p(hi);
+                double lam = dl < du ? dl : du;
+                double mu1 = (uy + ly - lam * (hi + lo)) / 2;
+                double mu2 = (uy - ly - lam * (hi - lo)) / 2;
+                z->c[i] = z->c[i] * lam + mu1;
+                for (int j = 0; j < p; j++) z->G[(size_t)j * n + i] = z->G[(size_t)j * n + i] * lam;
+                rows[q] = i; mus[q] = mu2; q++;
+            }
+        }
+    }
+    if (q > 0) {
+        z_reserve(z, p + q);
+        memset(z->G + (size_t)p * n, 0, sizeof(double) * (size_t)q * n);
+        for (int j = 0; j < q; j++) z->G[(size_t)(p + j) * n + rows[j]] = mus[j];
+        z->p = p + q;
+    }
+    z_remove_zero_columns(z);
+    free(rows); free(mus);
+    return q;
+}
+
+/* post kinds: 0 none, 1 shift (postb[0]), 2 scale (postA[0]), 3 matrix (post_rows x m), 4 project (post_dims) */
+typedef struct {
+    int pre_rows; const double* preA; const double* preb; /* affine preprocessing or pre_rows = 0 */
+    int post_kind; int post_rows; const double* postA; const double* postb; const int* post_dims;
+} clro_prepost;
+
+static int out_dim(const clro_net* net, const clro_prepost* pp) {
+    int m = net->dims[net->n_layers];
+    if (pp && (pp->post_kind == 3 || pp->post_kind == 4)) m = pp->post_rows;
+    return m;
+}
+
+/* controller_forward for one zonotope; result in *out (caller frees) */
+static void forward_one(const clro_net* net, const clro_prepost* pp, const zono* in, zono* out,
+                        int64_t* p_in, int64_t* unst, int64_t* near_thr) {
+    zono cur, nxt;
+    if (pp && pp->pre_rows > 0) {
+        z_affine(pp->preA, pp->preb, pp->pre_rows, in->n, in, &cur);
+    } else {
+        z_init(&cur, in->n, in->p);
+        memcpy(cur.c, in->c, sizeof(double) * in->n);
+        memcpy(cur.G, in->G, sizeof(double) * (size_t)in->n * in->p);
+        cur.p = in->p;
+    }
+    for (int l = 0; l < net->n_layers; l++) {
+        if (p_in) p_in[l] += cur.p;
+        z_affine(net->W[l], net->b[l], net->dims[l + 1], net->dims[l], &cur, &nxt);
+        z_free(&cur); cur = nxt;
+        int q = z_activation(&cur, net->act[l], near_thr);
+        if (unst) unst[l] += q;
+    }
+    if (pp && pp->post_kind == 1) {
+        for (int i = 0; i < cur.n; i++) cur.c[i] += pp->postb[0];
+    } else if (pp && pp->post_kind == 2) {
+        double a = pp->postA[0];
+        for (int i = 0; i < cur.n; i++) cur.c[i] = a * cur.c[i];
+        for (size_t e = 0; e < (size_t)cur.n * cur.p; e++) cur.G[e] = a * cur.G[e];
+    } else if (pp && pp->post_kind == 3) {
+        z_affine(pp->postA, NULL, pp->post_rows, cur.n, &cur, &nxt);
+        z_free(&cur); cur = nxt;
+    } else if (pp && pp->post_kind == 4) {
+        z_init(&nxt, pp->post_rows, cur.p);
+        for (int i = 0; i < pp->post_rows; i++) nxt.c[i] = cur.c[pp->post_dims[i]];
+        for (int j = 0; j < cur.p; j++)
+            for (int i = 0; i < pp->post_rows; i++)
+                nxt.G[(size_t)j * pp->post_rows + i] = cur.G[(size_t)j * cur.n + pp->post_dims[i]];
+        nxt.p = cur.p;
+        z_remove_zero_columns(&nxt);
+        z_free(&cur); cur = nxt;
+    }
+    *out = cur;
+}
+
+/* box of the output: 1-D -> Interval(low, high) (src/solve.jl:214-216), else box_approximation */
+static void z_box(const zono* z, double* lo, double* hi) {
+    if (z->n == 1) {
+        double l = z->c[0], h = z->c[0];
+        for (int j = 0; j < z->p; j++) { double a = fabs(z->G[j]); l -= a; h += a; }
+        lo[0] = l; hi[0] = h;
+        return;
+    }
+    for (int i = 0; i < z->n; i++) {
+        double r = 0.0;
+        for (int j = 0; j < z->p; j++) r += fabs(z->G[(size_t)j * z->n + i]);
+        lo[i] = z->c[i] - r; hi[i] = z->c[i] + r;
+    }
+}
+
+static void stats_merge(clro_stats* st, const clro_net* net, int64_t n_cells, const int64_t* p_in,
+                        const int64_t* unst, int64_t near_thr, int64_t max_p) {
+    if (!st) return;
+    memset(st, 0, sizeof(*st));
+    st->n_cells = n_cells; st->near_threshold = near_thr; st->max_p_out = max_p;
+    for (int l = 0; l < net->n_layers; l++) {
+        st->sum_p_in[l] = p_in[l]; st->sum_unstable[l] = unst[l];
+        st->flops += 2.0 * net->dims[l + 1] * net->dims[l] * ((double)p_in[l] + (double)n_cells);
+    }
+}
+
+/* Generic batched driver.  make_cell fills the input zonotope of cell i. */
+typedef void (*cell_fn)(void* ctx, int64_t i, zono* z);
+
+static int run_batch(const clro_net* net, const clro_prepost* pp, int64_t N, cell_fn make_cell, void* ctx,
+                     double* out_lo, double* out_hi, clro_stats* stats,
+                     int keep_cap, int32_t* out_ncols, double* out_c, double* out_G) {
+    int m = out_dim(net, pp);
+    int L = net->n_layers;
+    int64_t tp[CLRO_MAX_LAYERS] = {0}, tu[CLRO_MAX_LAYERS] = {0};
+    int64_t tnear = 0, tmax = 0;
+    int err = 0;
+#pragma omp parallel
+    {
+        int64_t lp[CLRO_MAX_LAYERS] = {0}, lu[CLRO_MAX_LAYERS] = {0};
+        int64_t lnear = 0, lmax = 0;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t i = 0; i < N; i++) {
+            zono in, out;
+            make_cell(ctx, i, &in);
+            forward_one(net, pp, &in, &out, lp, lu, &lnear);
+            if (out_lo) z_box(&out, out_lo + (size_t)i * m, out_hi + (size_t)i * m);
+            if (out.p > lmax) lmax = out.p;
+            if (keep_cap > 0) {
+                if (out.p > keep_cap) {
+#pragma omp atomic write
+                    err = 1;
+                } else {
+                    out_ncols[i] = out.p;
+                    memcpy(out_c + (size_t)i * m, out.c, sizeof(double) * m);
+                    memcpy(out_G + (size_t)i * m * keep_cap, out.G, sizeof(double) * (size_t)m * out.p);
+                }
+            }
+            z_free(&in); z_free(&out);
+        }
+#pragma omp critical
+        {
+            for (int l = 0; l < L; l++) { tp[l] += lp[l]; tu[l] += lu[l]; }
+            tnear += lnear; if (lmax > tmax) tmax = lmax;
+        }
+    }
+    stats_merge(stats, net, N, tp, tu, tnear, tmax);
+    return err ? -2 : 0;
+}
+
+/* ---- explicit zonotopes ------------------------------------------------------------------ */
+typedef struct { int n; const double* C; const int64_t* col_off; const double* G; } zbatch;
+static void cell_from_batch(void* ctx, int64_t i, zono* z) {
+    zbatch* b = (zbatch*)ctx;
+    int p = (int)(b->col_off[i + 1] - b->col_off[i]);
+    z_init(z, b->n, p);
+    memcpy(z->c, b->C + (size_t)i * b->n, sizeof(double) * b->n);
+    memcpy(z->G, b->G + (size_t)b->col_off[i] * b->n, sizeof(double) * (size_t)b->n * p);
+    z->p = p;
+}
+
+int clro_deepz_zonotopes(const clro_net* net, int n, int64_t N, const double* C, const int64_t* col_off,
+                         const double* G, const clro_prepost* pp, double* out_lo, double* out_hi,
+                         clro_stats* stats, int keep_cap, int32_t* out_ncols, double* out_c, double* out_G) {
+    zbatch b = {n, C, col_off, G};
+    return run_batch(net, pp, N, cell_from_batch, &b, out_lo, out_hi, stats, keep_cap, out_ncols, out_c, out_G);
+}
+
+/* ---- box grid: cells of split(H, partition) in product order (dimension 1 fastest) -------- */
+typedef struct { int n; const int32_t* part; const double* centers; const double* radii; int64_t begin; } gridctx;
+static void cell_from_grid(void* ctx, int64_t i, zono* z) {
+    gridctx* g = (gridctx*)ctx;
+    int64_t id = g->begin + i;
+    int n = g->n;
+    double r[64];
+    z_init(z, n, n);
+    int base = 0, p = 0;
+    for (int d = 0; d < n; d++) {
+        int k = (int)(id % g->part[d]); id /= g->part[d];
+        z->c[d] = g->centers[base + k];
+        r[d] = g->radii[base + k];
+        base += g->part[d];
+    }
+    /* convert(Zonotope, H): one generator r_d * e_d per non-flat dimension */
+    for (int d = 0; d < n; d++) {
+        if (r[d] != 0.0) {
+            memset(z->G + (size_t)p * n, 0, sizeof(double) * n);
+            z->G[(size_t)p * n + d] = r[d];
+            p++;
+        }
+    }
+    z->p = p;
+}
+
+int clro_deepz_boxgrid(const clro_net* net, int n, const int32_t* partition, const double* centers,
+                       const double* radii, int64_t cell_begin, int64_t cell_count, const clro_prepost* pp,
+                       double* out_lo, double* out_hi, clro_stats* stats,
+                       int keep_cap, int32_t* out_ncols, double* out_c, double* out_G) {
+    if (n > 64) return -1;
+    gridctx g = {n, partition, centers, radii, cell_begin};
+    return run_batch(net, pp, cell_count, cell_from_grid, &g, out_lo, out_hi, stats, keep_cap, out_ncols, out_c, out_G);
+}
+
+/* ---- pointwise forward(x, net)  (src/simulate.jl:101-106) --------------------------------- */
+static void forward_point(const clro_net* net, const clro_prepost* pp, const double* x, int nx, double* u,
+                          double* buf0, double* buf1) {
+    const double* cur = x;
+    int n = nx;
+    double* a = buf0; double* b = buf1;
+    if (pp && pp->pre_rows > 0) {
+        for (int i = 0; i < pp->pre_rows; i++) {
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s += pp->preA[(size_t)k * pp->pre_rows + i] * cur[k];
+            a[i] = s + pp->preb[i];
+        }
+        cur = a; n = pp->pre_rows; double* t = a; a = b; b = t;
+    }
+    for (int l = 0; l < net->n_layers; l++) {
+        int m = net->dims[l + 1];
+        for (int i = 0; i < m; i++) {
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s += net->W[l][(size_t)k * m + i] * cur[k];
+            s += net->b[l][i];
+            switch (net->act[l]) {
+                case 1: s = s > 0.0 ? s : 0.0; break;
+                case 2: s = 1.0 / (1.0 + exp(-s)); break;
+                case 3: s = tanh(s); break;
+                default: break;
+            }
+            a[i] = s;
+        }
+        cur = a; n = m; double* t = a; a = b; b = t;
+    }
+    int kind = pp ? pp->post_kind : 0;
+    if (kind == 3) {
+        for (int i = 0; i < pp->post_rows; i++) {
+            double s = 0.0;
+            for (int k = 0; k < n; k++) s += pp->postA[(size_t)k * pp->post_rows + i] * cur[k];
+            u[i] = s;
+        }
+    } else if (kind == 4) {
+        for (int i = 0; i < pp->post_rows; i++) u[i] = cur[pp->post_dims[i]];
+    } else {
+        for (int i = 0; i < n; i++)
+            u[i] = kind == 1 ? cur[i] + pp->postb[0] : (kind == 2 ? pp->postA[0] * cur[i] : cur[i]);
+    }
+}
+
+static int max_width(const clro_net* net, const clro_prepost* pp) {
+    int w = 1;
+    for (int l = 0; l <= net->n_layers; l++) if (net->dims[l] > w) w = net->dims[l];
+    if (pp && pp->pre_rows > w) w = pp->pre_rows;
+    if (pp && pp->post_rows > w) w = pp->post_rows;
+    return w;
+}
+
+int clro_forward_points(const clro_net* net, const clro_prepost* pp, int nx, int64_t N, const double* X, double* U) {
+    int m = out_dim(net, pp);
+    int w = max_width(net, pp);
+#pragma omp parallel
+    {
+        double* b0 = (double*)malloc(sizeof(double) * w);
+        double* b1 = (double*)malloc(sizeof(double) * w);
+#pragma omp for schedule(static)
+        for (int64_t j = 0; j < N; j++) forward_point(net, pp, X + (size_t)j * nx, nx, U + (size_t)j * m, b0, b1);
+        free(b0); free(b1);
+    }
+    return 0;
+}
+
+/* ---- plants (extended state [x; w; u], models/<name>/<name>.jl) ------------------------------- */
+enum { PLANT_UNICYCLE = 1, PLANT_TORA = 2, PLANT_ACC = 3, PLANT_INVPEND = 4 };
+
+static void plant_rhs(int plant, const double* x, double* dx, int n_ext) {
+    for (int i = 0; i < n_ext; i++) dx[i] = 0.0;
+    switch (plant) {
+        case PLANT_UNICYCLE: /* models/Unicycle/Unicycle.jl:36-47 */
+            dx[0] = x[3] * cos(x[2]);
+            dx[1] = x[3] * sin(x[2]);
+            dx[2] = x[6];
+            dx[3] = x[5] + x[4];
+            break;
+        case PLANT_TORA: /* models/TORA/TORA.jl:46-55 */
+            dx[0] = x[1];
+            dx[1] = -x[0] + (0.1 * sin(x[2]));
+            dx[2] = x[3];
+            dx[3] = x[4];
+            break;
+        case PLANT_ACC: /* models/ACC/ACC.jl:41-60 */
+            dx[0] = x[1];
+            dx[1] = x[2];
+            dx[2] = 2 * (-2.0 - x[2]) - 0.0001 * (x[1] * x[1]);
+            dx[3] = x[4];
+            dx[4] = x[5];
+            dx[5] = 2 * (x[6] - x[5]) - 0.0001 * (x[4] * x[4]);
+            break;
+        case PLANT_INVPEND: /* models/InvertedPendulum/InvertedPendulum.jl:44-51: gL = 2, mL = 8, c = 0 */
+            dx[0] = x[1];
+            dx[1] = 2.0 * sin(x[0]) + 8.0 * (x[2] - 0.0 * x[1]);
+            break;
+        default: break;
+    }
+}
+
+/* DiffEqBase fastpow (Float32 round trip; Goldberg log2 + fastapprox pow2), as recalled */
+static float fastlog2f(float x) {
+    const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+    uint32_t ux1i; memcpy(&ux1i, &x, 4);
+    uint32_t ex = (ux1i & 0x7F800000u) >> 23;
+    uint32_t greater = ux1i & 0x00400000u;
+    uint32_t ux2i; float signif, fexp;
+    if (greater) {
+        ux2i = (ux1i & 0x007FFFFFu) | 0x3f000000u;
+        memcpy(&signif, &ux2i, 4);
+        fexp = (float)ex - 126.0f;
+    } else {
+        ux2i = (ux1i & 0x007FFFFFu) | 0x3f800000u;
+        memcpy(&signif, &ux2i, 4);
+        fexp = (float)ex - 127.0f;
+    }
+    signif = signif - 1.0f;
+    return fexp + signif * (a * signif + b) / (signif + c);
+}
+static float fastpow2f(float x) {
+    float offset = x < 0 ? 1.0f : 0.0f;
+    float clipp = x < -126.0f ? -126.0f : x;
+    int32_t w = (int32_t)clipp;
+    float z = clipp - (float)w + offset;
+    float v = (float)(1 << 23) * (clipp + 121.2740575f + 27.7280233f / (4.84252568f - z) - 1.49012907f * z);
+    uint32_t vi = (uint32_t)v;
+    float r; memcpy(&r, &vi, 4);
+    return r;
+}
+static double pow_mode(double x, double y, int mode) {
+    if (mode == 0) return pow(x, y);
+    if (x == 0.0) return 0.0;
+    return (double)fastpow2f((float)y * fastlog2f((float)x));
+}
+
+static const double TS_c[6] __attribute__((unused)) = {0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+static const double TS_a[7][6] = {
+    {0},
+    {0.161},
+    {-0.008480655492356989, 0.335480655492357},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+static const double TS_bt[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
+                                -0.1447110071732629, 0.5823571654525552, -0.45808210592918697,
+                                0.015151515151515152};
+#define NEXT_MAX 32
+
+static double rms(const double* v, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += v[i] * v[i];
+    return sqrt(s / n);
+}
+static double eps_of(double x) { x = fabs(x); return nextafter(x, INFINITY) - x; }
+
+typedef struct { int32_t naccept, nreject; } stepinfo;
+
+/* One ODE.solve(prob, Tsit5()) over [t0, t1] with default tolerances/controller. */
+static stepinfo tsit5_solve(int plant, int n, double* u, double t0, double t1, double abstol, double reltol,
+                            int pmode, int log_cap, int32_t* log_n, double* log_t, double* log_u) {
+    const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0;
+    double k[7][NEXT_MAX], tmp[NEXT_MAX], unew[NEXT_MAX], sk[NEXT_MAX];
+    stepinfo info = {0, 0};
+    double t = t0, dtmax = t1 - t0;
+    int nlog = 0;
+    if (log_cap > 0) { log_t[0] = t; memcpy(log_u, u, sizeof(double) * n); nlog = 1; }
+    plant_rhs(plant, u, k[0], n);
+    /* ode_determine_initdt (order 5) */
+    double dt;
+    {
+        for (int i = 0; i < n; i++) sk[i] = abstol + fabs(u[i]) * reltol;
+        for (int i = 0; i < n; i++) tmp[i] = u[i] / sk[i];
+        double d0 = rms(tmp, n);
+        for (int i = 0; i < n; i++) tmp[i] = k[0][i] / sk[i];
+        double d1 = rms(tmp, n);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100;
+        if (dt0 > dtmax) dt0 = dtmax;
+        if (dt0 < 10 * 2.220446049250313e-16) {
+            dt = 1e-6;
+        } else {
+            for (int i = 0; i < n; i++) unew[i] = u[i] + dt0 * k[0][i];
+            plant_rhs(plant, unew, k[1], n);
+            for (int i = 0; i < n; i++) tmp[i] = (k[1][i] - k[0][i]) / sk[i];
+            double d2 = rms(tmp, n) / dt0;
+            double md = d1 > d2 ? d1 : d2;
+            double dt1 = md <= 1e-15 ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(md)) / 5);
+            dt = fmin(fmin(100 * dt0, dt1), dtmax);
+        }
+    }
+    double qold = 1e-4;
+    int guard = 0;
+    while (t < t1 && guard++ < 1000000) {
+        if (dt > t1 - t) dt = t1 - t; /* modify_dt_for_tstops! */
+        for (int s = 1; s <= 6; s++) {
+            for (int i = 0; i < n; i++) {
+                double acc = 0.0;
+                for (int j = 0; j < s; j++) acc += TS_a[s][j] * k[j][i];
+                tmp[i] = u[i] + dt * acc;
+            }
+            if (s < 6) plant_rhs(plant, tmp, k[s], n);
+        }
+        memcpy(unew, tmp, sizeof(double) * n);
+        plant_rhs(plant, unew, k[6], n);
+        for (int i = 0; i < n; i++) {
+            double e = 0.0;
+            for (int j = 0; j < 7; j++) e += TS_bt[j] * k[j][i];
+            e = dt * e;
+            tmp[i] = e / (abstol + fmax(fabs(u[i]), fabs(unew[i])) * reltol);
+        }
+        double EEst = rms(tmp, n);
+        double q, q11 = 0.0;
+        if (EEst == 0.0) {
+            q = 1.0 / qmax;
+        } else {
+            q11 = pow_mode(EEst, beta1, pmode);
+            q = q11 / pow_mode(qold, beta2, pmode);
+            q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / gamma));
+        }
+        if (EEst <= 1.0) {
+            info.naccept++;
+            qold = fmax(EEst, 1e-4);
+            double dtnew = dt / q;
+            double ttmp = t + dt;
+            if (fabs(ttmp - t1) < 100 * eps_of(fmax(t, t1))) ttmp = t1;
+            t = ttmp;
+            memcpy(u, unew, sizeof(double) * n);
+            memcpy(k[0], k[6], sizeof(double) * n);
+            dt = fmin(dtnew, dtmax);
+            if (log_cap > 0 && nlog < log_cap) {
+                log_t[nlog] = t; memcpy(log_u + (size_t)nlog * n, u, sizeof(double) * n); nlog++;
+            }
+        } else {
+            info.nreject++;
+            dt = dt / fmin(1.0 / qmin, q11 / gamma);
+        }
+    }
+    if (log_n) *log_n = nlog;
+    return info;
+}
+
+static void rk4_solve(int plant, int n, double* u, double t0, double t1, int substeps) {
+    double k1[NEXT_MAX], k2[NEXT_MAX], k3[NEXT_MAX], k4[NEXT_MAX], tmp[NEXT_MAX];
+    double dt = (t1 - t0) / substeps;
+    for (int s = 0; s < substeps; s++) {
+        plant_rhs(plant, u, k1, n);
+        for (int i = 0; i < n; i++) tmp[i] = u[i] + (dt / 2) * k1[i];
+        plant_rhs(plant, tmp, k2, n);
+        for (int i = 0; i < n; i++) tmp[i] = u[i] + (dt / 2) * k2[i];
+        plant_rhs(plant, tmp, k3, n);
+        for (int i = 0; i < n; i++) tmp[i] = u[i] + dt * k3[i];
+        plant_rhs(plant, tmp, k4, n);
+        for (int i = 0; i < n; i++) u[i] = u[i] + (dt / 6) * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+    }
+}
+
+/*
+ * simulate(): x0 (n_state x N), Wd (n_dist x N x iters), outputs X_end (n_state x N x iters),
+ * U (n_ctrl x N x iters); nsteps/nrej (N x iters) optional; optional step log for plotting pieces:
+ * log_cap points per trajectory-period, log_n (N x iters), log_t (log_cap x N x iters),
+ * log_u (n_ext x log_cap x N x iters).
+ */
+int clro_rollout(const clro_net* net, const clro_prepost* pp, int plant, int n_state, int n_dist, int n_ctrl,
+                 int64_t N, int iters, const double* x0, const double* Wd, double t0, double tau, double T,
+                 int alg, double abstol, double reltol, int substeps, int pmode,
+                 double* X_end, double* U, int32_t* nsteps, int32_t* nrej,
+                 int log_cap, int32_t* log_n, double* log_t, double* log_u) {
+    int n_ext = n_state + n_dist + n_ctrl;
+    if (n_ext > NEXT_MAX) return -1;
+    if (out_dim(net, pp) != n_ctrl) return -3;
+    int w = max_width(net, pp);
+#pragma omp parallel
+    {
+        double* b0 = (double*)malloc(sizeof(double) * w);
+        double* b1 = (double*)malloc(sizeof(double) * w);
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t j = 0; j < N; j++) {
+            double x[NEXT_MAX], ext[NEXT_MAX], u[NEXT_MAX];
+            memcpy(x, x0 + (size_t)j * n_state, sizeof(double) * n_state);
+            double t = t0;
+            for (int it = 0; it < iters; it++) {
+                forward_point(net, pp, x, n_state, u, b0, b1);
+                size_t cell = (size_t)it * N + j;
+                memcpy(U + cell * n_ctrl, u, sizeof(double) * n_ctrl);
+                memcpy(ext, x, sizeof(double) * n_state);
+                for (int d = 0; d < n_dist; d++) ext[n_state + d] = Wd[cell * n_dist + d];
+                memcpy(ext + n_state + n_dist, u, sizeof(double) * n_ctrl);
+                double t1 = it < iters - 1 ? t + tau : T;
+                if (alg == 0) {
+                    stepinfo si = tsit5_solve(plant, n_ext, ext, t, t1, abstol, reltol, pmode, log_cap,
+                                              log_n ? log_n + cell : NULL,
+                                              log_t ? log_t + cell * log_cap : NULL,
+                                              log_u ? log_u + cell * log_cap * n_ext : NULL);
+                    if (nsteps) nsteps[cell] = si.naccept;
+                    if (nrej) nrej[cell] = si.nreject;
+                } else {
+                    rk4_solve(plant, n_ext, ext, t, t1, substeps);
+                    if (nsteps) nsteps[cell] = substeps;
+                    if (nrej) nrej[cell] = 0;
+                }
+                memcpy(x, ext, sizeof(double) * n_state);
+                memcpy(X_end + cell * n_state, x, sizeof(double) * n_state);
+                t = t1;
+            }
+        }
+        free(b0); free(b1);
+    }
+    return 0;
+}

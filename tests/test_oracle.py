@@ -1,0 +1,164 @@
+"""CPU tests of the oracle itself: golden pins, the VerticalCAS KAT, structural properties."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_net
+from oracle import cbind, deepz_np as dz
+import vcas_kat
+
+TORA_LO, TORA_HI = [0.6, -0.7, -0.4, 0.5], [0.7, -0.6, -0.3, 0.6]
+
+
+def _tables(lo, hi, part):
+    cent, rad = dz.split_tables(lo, hi, part)
+    return cent, [np.full(len(c), r) for c, r in zip(cent, rad)]
+
+
+def test_vcas_verdicts_numpy_oracle():
+    nets = [load_net(f"VerticalCAS_{i}").as_tuples() for i in range(1, 10)]
+
+    def fh(adv, c, G):
+        c2, G2 = dz.deepz_forward(nets[adv], c, G)
+        return dz.low_high(c2, G2)[1]
+
+    for hdot0, want in vcas_kat.EXPECTED.items():
+        verdict, _ = vcas_kat.run_instance(hdot0, fh)
+        assert verdict == want, (hdot0, verdict)
+
+
+def test_vcas_verdicts_c_oracle():
+    nets = [cbind.Net(load_net(f"VerticalCAS_{i}").as_tuples()) for i in range(1, 10)]
+
+    def fh(adv, c, G):
+        r = cbind.deepz_zonotopes(nets[adv], c[None, :], [0, G.shape[1]], G.T)
+        return r["hi"][0]
+
+    for hdot0, want in vcas_kat.EXPECTED.items():
+        verdict, _ = vcas_kat.run_instance(hdot0, fh)
+        assert verdict == want, (hdot0, verdict)
+
+
+def test_tora_golden_numpy_and_c():
+    z = np.load(os.path.join(GOLDEN, "tora_oracle.npz"))
+    net = load_net("TORA_ReLU").as_tuples()
+    cn = cbind.Net(net)
+    for tag, part in (("p4435", [4, 4, 3, 5]), ("p1010101", [10, 10, 10, 1])):
+        cent, radii = _tables(TORA_LO, TORA_HI, part)
+        r = cbind.deepz_boxgrid(cn, part, cent, radii, post=("shift", -10.0))
+        np.testing.assert_allclose(r["lo"], z[f"{tag}_lo"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(r["hi"], z[f"{tag}_hi"], rtol=0, atol=1e-12)
+        assert r["stats"]["sum_p_in"] == list(z[f"{tag}_p_in"].sum(0))
+    l, h = dz.deepz_boxgrid(net, TORA_LO, TORA_HI, [4, 4, 3, 5], post=("shift", -10.0))
+    np.testing.assert_allclose(l, z["p4435_lo"], rtol=0, atol=1e-14)
+    # whole-X0 box gives u in [-0.2087, 0.2657]
+    assert abs(z["whole_lo"][0] + 0.2087) < 1e-4 and abs(z["whole_hi"][0] - 0.2657) < 1e-4
+
+
+def test_quadrotor_sigmoid_golden():
+    z = np.load(os.path.join(GOLDEN, "quadrotor_oracle.npz"))
+    net = load_net("Quadrotor").as_tuples()
+    cn = cbind.Net(net)
+    r = 0.01 * np.array([0.4] * 6 + [0.0] * 6)
+    part = [2] * 6 + [1] * 6
+    cent, radii = _tables(-r, r, part)
+    out = cbind.deepz_boxgrid(cn, part, cent, radii, keep_cap=256)
+    np.testing.assert_allclose(out["lo"], z["lo"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out["hi"], z["hi"], rtol=0, atol=1e-12)
+    p = out["ncols"][0]
+    assert p == z["cell0_G"].shape[1] == 6 + 64 * 3
+    # 1e-12 relative to the zonotope's scale: entries that are sums with cancellation cannot
+    # agree element-wise-relative across different (equally valid) summation orders
+    scale = np.abs(z["cell0_G"]).max()
+    np.testing.assert_allclose(out["G"][0, :p, :].T, z["cell0_G"], rtol=0, atol=1e-12 * scale)
+
+
+def test_degenerate_cell_equals_pointwise_forward():
+    """A zero-radius cell has no generators: DeepZ must equal pointwise forward (SURVEY 8c KAT 2)."""
+    rng = np.random.default_rng(1)
+    for name in ("TORA_ReLU", "ACC_tanh", "Quadrotor", "Unicycle"):
+        net = load_net(name).as_tuples()
+        n = net[0][0].shape[1]
+        x = rng.uniform(-1, 1, n)
+        c, G = dz.deepz_forward(net, x, np.zeros((n, 0)))
+        assert G.shape[1] == 0 or np.all(G == 0)
+        np.testing.assert_allclose(c, dz.forward_point(net, x), rtol=1e-13, atol=1e-15)
+        cn = cbind.Net(net)
+        r = cbind.deepz_zonotopes(cn, x[None, :], [0, 0], np.zeros((0, n)))
+        u = cbind.forward_points(cn, x[None, :])
+        np.testing.assert_allclose(r["lo"], u, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(r["hi"], u, rtol=1e-13, atol=1e-15)
+
+
+def test_soundness_by_sampling():
+    rng = np.random.default_rng(2)
+    for name, post in (("TORA_ReLU", ("shift", -10.0)), ("TORA_sigmoid", ("scale", 11.0)),
+                       ("TORA_ReLUtanh", ("scale", 11.0)), ("Unicycle", ("shift", -20.0))):
+        net = load_net(name).as_tuples()
+        n = net[0][0].shape[1]
+        c0 = rng.uniform(-0.5, 0.5, n)
+        r0 = rng.uniform(0.01, 0.05, n)
+        c, G = dz.hyperrectangle_to_zonotope(c0, r0)
+        _, _, lo, hi = dz.controller_forward(net, c, G, None, post)
+        xs = c0 + r0 * rng.uniform(-1, 1, (500, n))
+        us = np.array([dz.apply_post_point(post, dz.forward_point(net, x)) for x in xs])
+        assert np.all(us >= lo - 1e-12) and np.all(us <= hi + 1e-12)
+
+
+def test_hand_example_relu():
+    """2 -> 2 ReLU layer worked by hand: x in [-1,1]^2, y1 = x1 + x2 (unstable), y2 = x1 - x2 + 3 (active)."""
+    net = [(np.array([[1.0, 1.0], [1.0, -1.0]]), np.array([0.0, 3.0]), "ReLU")]
+    c, G = dz.hyperrectangle_to_zonotope([0.0, 0.0], [1.0, 1.0])
+    c2, G2 = dz.deepz_forward(net, c, G)
+    # neuron 1: l=-2,u=2 -> lambda=1/2, mu=1/2: c=0.5, row=[.5,.5], new generator 0.5
+    np.testing.assert_allclose(c2, [0.5, 3.0])
+    np.testing.assert_allclose(G2, [[0.5, 0.5, 0.5], [1.0, -1.0, 0.0]])
+
+
+def test_id_network_is_exact_affine_map():
+    """random_control_problems recipe (src/utils.jl:45-62): Id-only nets are exact affine maps."""
+    rng = np.random.default_rng(3)
+    W = 1.1 * (rng.random((3, 5)) - 0.5)
+    b = 0.1 * (rng.random(3) - 0.5)
+    c0, r0 = rng.random(5), rng.random(5)
+    c, G = dz.hyperrectangle_to_zonotope(c0, r0)
+    c2, G2 = dz.deepz_forward([(W, b, "Id")], c, G)
+    np.testing.assert_allclose(c2, W @ c0 + b, rtol=1e-15)
+    np.testing.assert_allclose(G2, W @ np.diag(r0), rtol=1e-15)
+
+
+def test_one_row_layer_collapses_to_single_generator():
+    net = load_net("TORA_ReLU").as_tuples()
+    c, G = dz.hyperrectangle_to_zonotope([0.65, -0.65, -0.35, 0.55], [0.05] * 4)
+    layers = []
+    dz.deepz_forward(net, c, G, layers_out=layers)
+    assert layers[-1][1].shape[1] <= 2  # one generator (+ one if the output ReLU is unstable)
+
+
+def test_split_order_dimension_one_fastest():
+    cells, rad = dz.split_box([0, 10, 100], [3, 12, 101], [3, 2, 1])
+    np.testing.assert_allclose(rad, [0.5, 0.5, 0.5])
+    np.testing.assert_allclose(cells[:, 0], [0.5, 1.5, 2.5, 0.5, 1.5, 2.5])
+    np.testing.assert_allclose(cells[:, 1], [10.5, 10.5, 10.5, 11.5, 11.5, 11.5])
+    for i in range(6):
+        idx = dz.cell_multi_index(i, [3, 2, 1])
+        assert idx == [i % 3, i // 3, 0]
+    with pytest.raises(ValueError):
+        dz.split_tables([0], [1], [0])
+
+
+def test_julia_range_rationalisation():
+    # 0.605:0.01 -> exact decimals k/200, e.g. element 2 is the double nearest 0.625
+    r = dz.julia_range(0.605, 0.01, 10)
+    assert r[2] == 0.625 and r[0] == 0.605 and r[9] == 0.695
+
+
+def test_c_oracle_threads_and_flops():
+    assert cbind.num_threads() >= 1
+    net = load_net("TORA_ReLU").as_tuples()
+    cn = cbind.Net(net)
+    cent, radii = _tables(TORA_LO, TORA_HI, [10, 10, 10, 1])
+    r = cbind.deepz_boxgrid(cn, [10, 10, 10, 1], cent, radii, post=("shift", -10.0))
+    # mean 0.327 MFLOP per cell on this workload
+    assert abs(r["stats"]["flops"] / 1000 / 1e6 - 0.327) < 0.002
