@@ -1,0 +1,878 @@
+// clr_api.cu -- host side of libclr_b200.so: the C ABI declared in include/clr_b200.h.
+//
+// Everything here is plumbing around the kernels in deepz.cuh / rollout.cuh: device buffers,
+// the folding of pre/post-processing (src/problem.jl:5-77) into extra affine layers, the DMMA
+// fragment layout of the weights, the launch sequence (main pass -> retry pass -> big-cell pass)
+// and the host <-> device copies of the blocking (non CLR_FLAG_DEVICE_IO) mode.
+// There is no CPU fallback: without a device clr_create fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "deepz.cuh"
+#include "rollout.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostLayer {
+    int n, m, act, collapse, net_layer, project = 0;
+    std::vector<double> W;   // m x n column-major
+    std::vector<double> b;   // m
+};
+
+struct Compiled {            // one (network, pre/post-processing) pair on the device
+    std::vector<unsigned char> key;
+    std::vector<void*> allocs;
+    DevNet host{};
+    DevNet* dev = nullptr;
+    PointNet pnet{};
+    int ksreg = 8;
+    int warps = 8;
+    int stored_width = 0;
+    int worst_cols_growth = 0;
+};
+
+}  // namespace
+
+struct clr_net {
+    clr_ctx* ctx;
+    int L;
+    std::vector<int> dims, act;
+    std::vector<std::vector<double>> W, b;
+    Compiled* compiled = nullptr;
+};
+
+struct clr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sms = 0;
+    int smem_optin = 0;
+    int tile_cells = 0;
+    DevCallState* d_state = nullptr;
+    DevCallState* h_state = nullptr;     // pinned
+    long long* d_retry = nullptr;
+    long long* d_big = nullptr;
+    int64_t list_cap = 0;
+    double* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    // scratch for blocking-mode I/O
+    void* d_io[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t io_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double* d_hull = nullptr;            // 2 * m_out
+    int hull_cap = 0;
+    // kept output zonotopes
+    int* d_keepN = nullptr;
+    double* d_keepC = nullptr;
+    double* d_keepG = nullptr;
+    size_t keepN_bytes = 0, keepC_bytes = 0, keepG_bytes = 0;
+    int64_t keep_cells = 0;
+    int keep_cap = 0, keep_m = 0;
+    int* d_err = nullptr;
+};
+
+namespace {
+
+int fail(clr_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, CLR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                         \
+    } while (0)
+
+int ensure(clr_ctx* ctx, void** p, size_t* have, size_t need) {
+    if (need <= *have && *p) return 0;
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr; *have = 0;
+    size_t sz = need + need / 4 + 256;
+    CU(cudaMalloc(p, sz));
+    *have = sz;
+    return 0;
+}
+
+__global__ void fill_hull_kernel(double* hull, int m) {
+    int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i < m) { hull[i] = INFINITY; hull[m + i] = -INFINITY; }
+}
+
+__global__ void max_cols_kernel(const long long* col_off, long long N, int* out) {
+    int best = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        int p = (int)(col_off[i + 1] - col_off[i]);
+        best = p > best ? p : best;
+    }
+    atomicMax(out, best);
+}
+
+void free_compiled(Compiled* c) {
+    if (!c) return;
+    for (void* p : c->allocs) cudaFree(p);
+    delete c;
+}
+
+// The layer list the kernels run: [pre] + network + [post]   (src/solve.jl:211-213)
+int fold_layers(clr_ctx* ctx, const clr_net* net, const clr_prepost* pp, int n_in, std::vector<HostLayer>& out) {
+    int cur = n_in;
+    if (pp && pp->pre_rows > 0) {
+        if (!pp->preA || !pp->preb) return fail(ctx, CLR_ERR_ARG, "pre_rows > 0 needs preA and preb");
+        HostLayer h;
+        h.n = n_in; h.m = pp->pre_rows; h.act = CLR_ACT_ID; h.collapse = pp->pre_rows == 1; h.net_layer = -1;
+        h.W.assign(pp->preA, pp->preA + (size_t)h.m * h.n);
+        h.b.assign(pp->preb, pp->preb + h.m);
+        out.push_back(std::move(h));
+        cur = pp->pre_rows;
+    }
+    if (cur != net->dims[0])
+        return fail(ctx, CLR_ERR_DIM, "input dimension %d does not match the network input dimension %d", cur, net->dims[0]);
+    for (int l = 0; l < net->L; l++) {
+        HostLayer h;
+        h.n = net->dims[l]; h.m = net->dims[l + 1]; h.act = net->act[l]; h.collapse = h.m == 1; h.net_layer = l;
+        h.W = net->W[l]; h.b = net->b[l];
+        out.push_back(std::move(h));
+    }
+    const int m = net->dims[net->L];
+    const int kind = pp ? pp->post_kind : CLR_POST_NONE;
+    if (kind == CLR_POST_SHIFT || kind == CLR_POST_SCALE) {
+        if ((kind == CLR_POST_SHIFT && !pp->postb) || (kind == CLR_POST_SCALE && !pp->postA))
+            return fail(ctx, CLR_ERR_ARG, "post-processing value missing");
+        HostLayer h;
+        h.n = m; h.m = m; h.act = CLR_ACT_ID; h.collapse = 0; h.net_layer = -1;
+        h.W.assign((size_t)m * m, 0.0);
+        h.b.assign(m, kind == CLR_POST_SHIFT ? pp->postb[0] : 0.0);
+        for (int i = 0; i < m; i++) h.W[(size_t)i * m + i] = kind == CLR_POST_SHIFT ? 1.0 : pp->postA[0];
+        out.push_back(std::move(h));
+    } else if (kind == CLR_POST_MATRIX) {
+        if (!pp->postA || pp->post_rows < 1) return fail(ctx, CLR_ERR_ARG, "post matrix missing");
+        HostLayer h;
+        h.n = m; h.m = pp->post_rows; h.act = CLR_ACT_ID; h.collapse = h.m == 1; h.net_layer = -1;
+        h.W.assign(pp->postA, pp->postA + (size_t)h.m * m);
+        h.b.assign(h.m, 0.0);
+        out.push_back(std::move(h));
+    } else if (kind == CLR_POST_PROJECT) {
+        if (!pp->post_dims || pp->post_rows < 1) return fail(ctx, CLR_ERR_ARG, "post projection dims missing");
+        HostLayer h;
+        h.n = m; h.m = pp->post_rows; h.act = CLR_ACT_ID; h.collapse = 0; h.net_layer = -1; h.project = 1;
+        h.W.assign((size_t)h.m * m, 0.0);
+        h.b.assign(h.m, 0.0);
+        for (int i = 0; i < h.m; i++) {
+            int d = pp->post_dims[i];
+            if (d < 0 || d >= m) return fail(ctx, CLR_ERR_DIM, "projection dimension %d out of range", d);
+            h.W[(size_t)d * h.m + i] = 1.0;
+        }
+        out.push_back(std::move(h));
+    } else if (kind != CLR_POST_NONE) {
+        return fail(ctx, CLR_ERR_ARG, "unknown post_kind %d", kind);
+    }
+    return 0;
+}
+
+std::vector<unsigned char> prepost_key(const clr_net* net, const clr_prepost* pp, int n_in) {
+    std::vector<unsigned char> k;
+    auto put = [&](const void* p, size_t n) { const unsigned char* c = (const unsigned char*)p; k.insert(k.end(), c, c + n); };
+    put(&n_in, sizeof(int));
+    if (!pp) return k;
+    put(&pp->pre_rows, sizeof(int));
+    put(&pp->post_kind, sizeof(int));
+    put(&pp->post_rows, sizeof(int));
+    if (pp->pre_rows > 0 && pp->preA && pp->preb) {
+        put(pp->preA, sizeof(double) * (size_t)pp->pre_rows * n_in);
+        put(pp->preb, sizeof(double) * pp->pre_rows);
+    }
+    const int m = net->dims[net->L];
+    if (pp->post_kind == CLR_POST_SHIFT && pp->postb) put(pp->postb, sizeof(double));
+    if (pp->post_kind == CLR_POST_SCALE && pp->postA) put(pp->postA, sizeof(double));
+    if (pp->post_kind == CLR_POST_MATRIX && pp->postA) put(pp->postA, sizeof(double) * (size_t)pp->post_rows * m);
+    if (pp->post_kind == CLR_POST_PROJECT && pp->post_dims) put(pp->post_dims, sizeof(int) * pp->post_rows);
+    return k;
+}
+
+template <typename T>
+int upload(clr_ctx* ctx, Compiled* c, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t bytes = sizeof(T) * (v.empty() ? 1 : v.size());
+    CU(cudaMalloc(&p, bytes));
+    c->allocs.push_back(p);
+    if (!v.empty()) CU(cudaMemcpyAsync(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = (const T*)p;
+    return 0;
+}
+
+int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Compiled** outc) {
+    std::vector<unsigned char> key = prepost_key(net, pp, n_in);
+    if (net->compiled && net->compiled->key == key) { *outc = net->compiled; return 0; }
+    std::vector<HostLayer> layers;
+    int rc = fold_layers(ctx, net, pp, n_in, layers);
+    if (rc) return rc;
+    if ((int)layers.size() > CLR_DEV_MAX_LAYERS) return fail(ctx, CLR_ERR_ARG, "too many layers");
+    Compiled* c = new Compiled();
+    c->key = key;
+    DevNet& D = c->host;
+    D.L = (int)layers.size();
+    D.n_in = n_in;
+    D.m_out = layers.back().m;
+    D.max_rows = n_in;
+    D.max_pitch = clr_pitch(n_in);
+    int maxKsReg = 1, maxRB = 1;
+    PointNet& P = c->pnet;
+    P.L = D.L; P.n_in = n_in; P.m_out = D.m_out;
+    P.dims[0] = n_in;
+    std::vector<double> image;
+    for (int l = 0; l < D.L; l++) {
+        const HostLayer& h = layers[l];
+        if (h.m > CLR_MAX_ROWS || h.n > CLR_MAX_ROWS * 8) {
+            free_compiled(c);
+            return fail(ctx, CLR_ERR_ARG, "layer %d is %d x %d; this build supports at most %d rows", l, h.m, h.n, CLR_MAX_ROWS);
+        }
+        DevLayer& d = D.layer[l];
+        d.n = h.n; d.m = h.m;
+        d.ksteps = (h.n + 3) / 4;
+        d.rblocks = (h.m + 7) / 8;
+        d.pitch_in = l == 0 ? clr_pitch(n_in) : D.layer[l - 1].pitch_out;
+        d.pitch_out = clr_pitch(h.m);
+        d.act = h.act; d.collapse = h.collapse; d.net_layer = h.net_layer;
+        d.remove_zero = h.act != CLR_ACT_ID || h.project;
+        D.max_rows = std::max(D.max_rows, h.m);
+        D.max_pitch = std::max(D.max_pitch, d.pitch_out);
+        if (d.ksteps <= 32) maxKsReg = std::max(maxKsReg, d.ksteps);
+        maxRB = std::max(maxRB, d.rblocks);
+        // DMMA A fragments: [rb][ks][lane] = W[rb*8 + lane/4][ks*4 + lane%4]
+        std::vector<double> af((size_t)d.rblocks * d.ksteps * 32, 0.0);
+        for (int rb = 0; rb < d.rblocks; rb++)
+            for (int ks = 0; ks < d.ksteps; ks++)
+                for (int lane = 0; lane < 32; lane++) {
+                    int r = rb * 8 + (lane >> 2), k = ks * 4 + (lane & 3);
+                    if (r < h.m && k < h.n) af[((size_t)rb * d.ksteps + ks) * 32 + lane] = h.W[(size_t)k * h.m + r];
+                }
+        if ((rc = upload(ctx, c, af, &d.Afrag))) { free_compiled(c); return rc; }
+        if ((rc = upload(ctx, c, h.b, &d.bias))) { free_compiled(c); return rc; }
+        if ((rc = upload(ctx, c, h.W, &d.Wcm))) { free_compiled(c); return rc; }
+        // pointwise image: row-major W, column-major W, bias
+        P.dims[l + 1] = h.m; P.act[l] = h.act;
+        P.off_rm[l] = (int)image.size();
+        for (int i = 0; i < h.m; i++) for (int k = 0; k < h.n; k++) image.push_back(h.W[(size_t)k * h.m + i]);
+        P.off_cm[l] = (int)image.size();
+        image.insert(image.end(), h.W.begin(), h.W.end());
+        P.off_b[l] = (int)image.size();
+        image.insert(image.end(), h.b.begin(), h.b.end());
+        P.Wcm[l] = d.Wcm; P.b[l] = d.bias; P.Wrm[l] = nullptr;
+    }
+    P.total_doubles = (int)image.size();
+    if ((rc = upload(ctx, c, image, &P.image))) { free_compiled(c); return rc; }
+    c->stored_width = ro_stored_width(P.dims, P.L);
+    const int ks_opts[4] = {8, 16, 25, 32};
+    c->ksreg = 32;
+    for (int o = 0; o < 4; o++) if (maxKsReg <= ks_opts[o]) { c->ksreg = ks_opts[o]; break; }
+    c->warps = maxRB >= 16 ? 16 : maxRB * (16 / maxRB);
+    if (c->warps < 4) c->warps = 4;
+    {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, sizeof(DevNet));
+        if (e != cudaSuccess) { free_compiled(c); return fail(ctx, CLR_ERR_CUDA, "cudaMalloc(DevNet): %s", cudaGetErrorString(e)); }
+        c->allocs.push_back(p);
+        c->dev = (DevNet*)p;
+        e = cudaMemcpy(p, &D, sizeof(DevNet), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { free_compiled(c); return fail(ctx, CLR_ERR_CUDA, "cudaMemcpy(DevNet): %s", cudaGetErrorString(e)); }
+    }
+    free_compiled(net->compiled);
+    net->compiled = c;
+    *outc = c;
+    return 0;
+}
+
+// worst-case columns of one cell anywhere in the network, given p0 input generators
+int worst_cols(const DevNet& D, int p0) {
+    int p = p0, worst = 1 + p0;
+    for (int l = 0; l < D.L; l++) {
+        const DevLayer& d = D.layer[l];
+        if (d.collapse) p = 1;
+        if (d.act != CLR_ACT_ID) p += d.m;
+        worst = std::max(worst, 1 + p);
+    }
+    return worst;
+}
+
+template <int KSREG, bool GLOBAL, bool STATS>
+int launch_deepz_t(clr_ctx* ctx, int grid, int threads, size_t smem, const DevNet* net, const DeepzInput& in,
+                   const DeepzOutput& out, const DeepzSched& sp) {
+    auto kern = deepz_kernel<KSREG, GLOBAL, STATS>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, ctx->stream>>>(net, in, out, ctx->d_state, sp);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+template <bool GLOBAL, bool STATS>
+int launch_deepz_k(clr_ctx* ctx, int ksreg, int grid, int threads, size_t smem, const DevNet* net,
+                   const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
+    switch (ksreg) {
+        case 8: return launch_deepz_t<8, GLOBAL, STATS>(ctx, grid, threads, smem, net, in, out, sp);
+        case 16: return launch_deepz_t<16, GLOBAL, STATS>(ctx, grid, threads, smem, net, in, out, sp);
+        case 25: return launch_deepz_t<25, GLOBAL, STATS>(ctx, grid, threads, smem, net, in, out, sp);
+        default: return launch_deepz_t<32, GLOBAL, STATS>(ctx, grid, threads, smem, net, in, out, sp);
+    }
+}
+
+int launch_deepz(clr_ctx* ctx, bool global, bool stats, int ksreg, int grid, int threads, size_t smem,
+                 const DevNet* net, const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
+    if (global) return stats ? launch_deepz_k<true, true>(ctx, ksreg, grid, threads, smem, net, in, out, sp)
+                             : launch_deepz_k<true, false>(ctx, ksreg, grid, threads, smem, net, in, out, sp);
+    return stats ? launch_deepz_k<false, true>(ctx, ksreg, grid, threads, smem, net, in, out, sp)
+                 : launch_deepz_k<false, false>(ctx, ksreg, grid, threads, smem, net, in, out, sp);
+}
+
+// Shared driver of clr_deepz_boxgrid / clr_deepz_zonotopes once `in` points at device inputs.
+int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max, double* out_lo, double* out_hi,
+              double* hull_lo, double* hull_hi, clr_stats* stats, int keep_cap, int flags) {
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    const bool want_stats = stats != nullptr && !(flags & CLR_FLAG_NO_STATS);
+    const DevNet& D = c->host;
+    const int m = D.m_out;
+    const long long N = in.N;
+    if (keep_cap < 0) return fail(ctx, CLR_ERR_ARG, "keep_cap < 0");
+    if (want_stats) memset(stats, 0, sizeof(*stats));
+    if (N == 0) {
+        if (stats) { memset(stats, 0, sizeof(*stats)); }
+        if (!dev_io && hull_lo) for (int i = 0; i < m; i++) { hull_lo[i] = INFINITY; hull_hi[i] = -INFINITY; }
+        ctx->keep_cells = 0;
+        return 0;
+    }
+    // device outputs
+    DeepzOutput out{};
+    out.keep_cap = keep_cap;
+    if (dev_io) {
+        out.out_lo = out_lo; out.out_hi = out_hi;
+    }
+    if (m > ctx->hull_cap) {
+        if (ctx->d_hull) CU(cudaFree(ctx->d_hull));
+        ctx->d_hull = nullptr;
+        CU(cudaMalloc((void**)&ctx->d_hull, sizeof(double) * 2 * m));
+        ctx->hull_cap = m;
+    }
+    const bool want_hull = hull_lo != nullptr && hull_hi != nullptr;
+    if (want_hull) {
+        fill_hull_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_hull, m);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        out.hull_lo = ctx->d_hull; out.hull_hi = ctx->d_hull + m;
+    } else {
+        out.hull_lo = nullptr; out.hull_hi = nullptr;
+    }
+    if (!dev_io) {
+        if (out_lo && out_hi) {
+            int rc;
+            if ((rc = ensure(ctx, &ctx->d_io[4], &ctx->io_bytes[4], sizeof(double) * (size_t)m * N))) return rc;
+            if ((rc = ensure(ctx, &ctx->d_io[5], &ctx->io_bytes[5], sizeof(double) * (size_t)m * N))) return rc;
+            out.out_lo = (double*)ctx->d_io[4]; out.out_hi = (double*)ctx->d_io[5];
+        } else {
+            out.out_lo = nullptr; out.out_hi = nullptr;
+        }
+    }
+    if (keep_cap > 0) {
+        int rc;
+        if ((rc = ensure(ctx, (void**)&ctx->d_keepN, &ctx->keepN_bytes, sizeof(int) * (size_t)N))) return rc;
+        if ((rc = ensure(ctx, (void**)&ctx->d_keepC, &ctx->keepC_bytes, sizeof(double) * (size_t)m * N))) return rc;
+        if ((rc = ensure(ctx, (void**)&ctx->d_keepG, &ctx->keepG_bytes, sizeof(double) * (size_t)m * keep_cap * N))) return rc;
+        out.keepN = ctx->d_keepN; out.keepC = ctx->d_keepC; out.keepG = ctx->d_keepG;
+    }
+    ctx->keep_cells = 0;
+    // scheduler state and lists
+    if (N > ctx->list_cap) {
+        if (ctx->d_retry) CU(cudaFree(ctx->d_retry));
+        if (ctx->d_big) CU(cudaFree(ctx->d_big));
+        ctx->d_retry = ctx->d_big = nullptr; ctx->list_cap = 0;
+        CU(cudaMalloc((void**)&ctx->d_retry, sizeof(long long) * (size_t)N));
+        CU(cudaMalloc((void**)&ctx->d_big, sizeof(long long) * (size_t)N));
+        ctx->list_cap = N;
+    }
+    CU(cudaMemsetAsync(ctx->d_state, 0, sizeof(DevCallState), ctx->stream));
+
+    const int threads = c->warps * 32;
+    const size_t meta = dz_meta_bytes(want_stats);
+    const size_t smem_total = (size_t)ctx->smem_optin;
+    if (smem_total < meta + 2 * 8 * 64) return fail(ctx, CLR_ERR_CUDA, "device has too little shared memory");
+    DeepzSched sp{};
+    sp.cap = (int)((smem_total - meta) / 16);
+    sp.tile_cells = ctx->tile_cells;
+    sp.items_cells = std::max(1, DZ_IMAX * threads / clr_pad4(D.max_rows));
+    sp.retry_list = ctx->d_retry;
+    sp.big_list = ctx->d_big;
+    sp.workspace = nullptr;
+    int grid = (int)std::min<long long>(ctx->sms, N);
+    int rc;
+    sp.pass = 0;
+    if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 16, c->dev, in, out, sp))) return rc;
+    sp.pass = 1;
+    if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 16, c->dev, in, out, sp))) return rc;
+    // how many cells did not fit in shared memory at all?
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_state->n_big > 0) {
+        const int wc = worst_cols(D, p0max);
+        DeepzSched sg = sp;
+        sg.pass = 2;
+        sg.cap = (wc + 8) * D.max_pitch;
+        int gridg = (int)std::min<unsigned long long>((unsigned long long)ctx->sms, ctx->h_state->n_big);
+        size_t need = sizeof(double) * (size_t)gridg * 2 * sg.cap;
+        if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, need))) return rc;
+        sg.workspace = ctx->d_ws;
+        if ((rc = launch_deepz(ctx, true, want_stats, c->ksreg, gridg, threads, dz_meta_bytes(want_stats), c->dev, in, out, sg))) return rc;
+        CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (ctx->h_state->error == CLR_ERR_CAPACITY && keep_cap > 0)
+        return fail(ctx, CLR_ERR_CAPACITY, "an output zonotope has more than keep_cap = %d generators (max_p_out = %d)", keep_cap,
+                    ctx->h_state->max_p_out);
+    if (ctx->h_state->error) return fail(ctx, ctx->h_state->error, "device-side error %d in the DeepZ kernel", ctx->h_state->error);
+    if (want_stats) {
+        const DevCallState& s = *ctx->h_state;
+        stats->n_cells = N;
+        stats->near_threshold = (int64_t)s.near_threshold;
+        stats->max_p_out = s.max_p_out;
+        for (int l = 0; l < net->L; l++) {
+            stats->sum_p_in[l] = (int64_t)s.sum_p_in[l];
+            stats->sum_unstable[l] = (int64_t)s.sum_unstable[l];
+            stats->flops += 2.0 * net->dims[l + 1] * net->dims[l] * ((double)s.sum_p_in[l] + (double)N);
+        }
+    }
+    if (keep_cap > 0) { ctx->keep_cells = N; ctx->keep_cap = keep_cap; ctx->keep_m = m; }
+    // results
+    if (dev_io) {
+        if (want_hull) {
+            CU(cudaMemcpyAsync(hull_lo, ctx->d_hull, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(hull_hi, ctx->d_hull + m, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    } else {
+        if (out_lo && out_hi) {
+            CU(cudaMemcpyAsync(out_lo, out.out_lo, sizeof(double) * (size_t)m * N, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(out_hi, out.out_hi, sizeof(double) * (size_t)m * N, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (want_hull) {
+            CU(cudaMemcpyAsync(hull_lo, ctx->d_hull, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(hull_hi, ctx->d_hull + m, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int stage_in(clr_ctx* ctx, int slot, const void* src, size_t bytes, bool dev_io, const void** out) {
+    if (dev_io) { *out = src; return 0; }
+    int rc = ensure(ctx, &ctx->d_io[slot], &ctx->io_bytes[slot], bytes ? bytes : 8);
+    if (rc) return rc;
+    if (bytes) CU(cudaMemcpyAsync(ctx->d_io[slot], src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *out = ctx->d_io[slot];
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int32_t clr_create(int32_t device, clr_ctx** out) {
+    clr_ctx* ctx = nullptr;   // errors before the ctx exists go to the thread-local message
+    if (!out) return fail(nullptr, CLR_ERR_ARG, "clr_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, CLR_ERR_CUDA, "no CUDA device available (%s); libclr_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, CLR_ERR_ARG, "device %d out of range (0..%d)", device, count - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, CLR_ERR_CUDA, "device %d is sm_%d%d; libclr_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    clr_ctx* c = new clr_ctx();
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state, sizeof(DevCallState));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(DevCallState));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_err, sizeof(int));
+    if (e != cudaSuccess) {
+        int rc = fail(nullptr, CLR_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+void clr_destroy(clr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_state);
+    cudaFreeHost(ctx->h_state);
+    cudaFree(ctx->d_retry);
+    cudaFree(ctx->d_big);
+    cudaFree(ctx->d_ws);
+    for (int i = 0; i < 8; i++) cudaFree(ctx->d_io[i]);
+    cudaFree(ctx->d_hull);
+    cudaFree(ctx->d_keepN);
+    cudaFree(ctx->d_keepC);
+    cudaFree(ctx->d_keepG);
+    cudaFree(ctx->d_err);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* clr_last_error(const clr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void* clr_stream(clr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int32_t clr_synchronize(clr_ctx* ctx) {
+    if (!ctx) return CLR_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int64_t clr_launch_count(const clr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t clr_device_alloc(clr_ctx* ctx, int64_t bytes, void** out) {
+    if (!ctx || !out || bytes < 0) return fail(ctx, CLR_ERR_ARG, "clr_device_alloc: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(out, (size_t)(bytes ? bytes : 8)));
+    return 0;
+}
+int32_t clr_device_free(clr_ctx* ctx, void* p) {
+    if (!ctx) return CLR_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(p));
+    return 0;
+}
+int32_t clr_memcpy_h2d(clr_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx) return CLR_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int32_t clr_memcpy_d2h(clr_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx) return CLR_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells) {
+    if (!ctx || cells < 0 || cells > CLR_TILE_CELLS_MAX) return fail(ctx, CLR_ERR_ARG, "tile cells must be in 0..%d", CLR_TILE_CELLS_MAX);
+    ctx->tile_cells = cells;
+    return 0;
+}
+
+int32_t clr_net_upload(clr_ctx* ctx, int32_t n_layers, const int32_t* dims, const int32_t* act,
+                       const double* const* W, const double* const* b, clr_net** out) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (!out || !dims || !act || !W || !b) return fail(ctx, CLR_ERR_ARG, "clr_net_upload: NULL argument");
+    *out = nullptr;
+    if (n_layers < 1 || n_layers > CLR_MAX_LAYERS) return fail(ctx, CLR_ERR_ARG, "n_layers must be in 1..%d", CLR_MAX_LAYERS);
+    for (int l = 0; l <= n_layers; l++) if (dims[l] < 1) return fail(ctx, CLR_ERR_DIM, "dims[%d] = %d", l, dims[l]);
+    for (int l = 0; l < n_layers; l++) {
+        if (act[l] < CLR_ACT_ID || act[l] > CLR_ACT_TANH) return fail(ctx, CLR_ERR_ARG, "unknown activation %d in layer %d", act[l], l);
+        if (!W[l] || !b[l]) return fail(ctx, CLR_ERR_ARG, "layer %d has NULL weights", l);
+        if (dims[l + 1] > CLR_MAX_ROWS) return fail(ctx, CLR_ERR_ARG, "layer %d has %d neurons; at most %d supported", l, dims[l + 1], CLR_MAX_ROWS);
+    }
+    clr_net* net = new clr_net();
+    net->ctx = ctx;
+    net->L = n_layers;
+    net->dims.assign(dims, dims + n_layers + 1);
+    net->act.assign(act, act + n_layers);
+    for (int l = 0; l < n_layers; l++) {
+        net->W.emplace_back(W[l], W[l] + (size_t)dims[l + 1] * dims[l]);
+        net->b.emplace_back(b[l], b[l] + dims[l + 1]);
+    }
+    *out = net;
+    return 0;
+}
+
+void clr_net_free(clr_net* net) {
+    if (!net) return;
+    if (net->ctx) cudaSetDevice(net->ctx->device);
+    free_compiled(net->compiled);
+    delete net;
+}
+
+int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net_c, int32_t n, const int32_t* partition,
+                          const double* centers, const double* radii, int64_t cell_begin,
+                          int64_t cell_count, const clr_prepost* pp, double* out_lo, double* out_hi,
+                          double* hull_lo, double* hull_hi, clr_stats* stats, int32_t keep_cap,
+                          int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    clr_net* net = const_cast<clr_net*>(net_c);
+    if (!net || !partition || !centers || !radii) return fail(ctx, CLR_ERR_ARG, "clr_deepz_boxgrid: NULL argument");
+    if (n < 1 || n > 64) return fail(ctx, CLR_ERR_DIM, "box dimension %d not in 1..64", n);
+    CU(cudaSetDevice(ctx->device));
+    long double total = 1;
+    int tab = 0;
+    DeepzInput in{};
+    for (int d = 0; d < n; d++) {
+        if (partition[d] < 1) return fail(ctx, CLR_ERR_ARG, "partition[%d] = %d: each dimension needs at least one block", d, partition[d]);
+        in.part[d] = partition[d]; in.base[d] = tab;
+        tab += partition[d];
+        total *= partition[d];
+    }
+    if (cell_begin < 0 || cell_count < 0 || (long double)cell_begin + (long double)cell_count > total)
+        return fail(ctx, CLR_ERR_ARG, "cell range [%lld, %lld) outside the split", (long long)cell_begin, (long long)(cell_begin + cell_count));
+    Compiled* c = nullptr;
+    int rc = compile_net(ctx, net, pp, n, &c);
+    if (rc) return rc;
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    const void *dc, *dr;
+    if ((rc = stage_in(ctx, 0, centers, sizeof(double) * tab, dev_io, &dc))) return rc;
+    if ((rc = stage_in(ctx, 1, radii, sizeof(double) * tab, dev_io, &dr))) return rc;
+    in.kind = 0; in.n = n; in.N = cell_count; in.cell_begin = cell_begin;
+    in.centers = (const double*)dc; in.radii = (const double*)dr;
+    return run_deepz(ctx, net, c, in, n, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags);
+}
+
+int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net_c, int32_t n, int64_t N, const double* C,
+                            const int64_t* col_off, const double* G, const clr_prepost* pp,
+                            double* out_lo, double* out_hi, double* hull_lo, double* hull_hi,
+                            clr_stats* stats, int32_t keep_cap, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    clr_net* net = const_cast<clr_net*>(net_c);
+    if (!net || N < 0 || n < 1) return fail(ctx, CLR_ERR_ARG, "clr_deepz_zonotopes: bad argument");
+    if (N > 0 && (!C || !col_off)) return fail(ctx, CLR_ERR_ARG, "clr_deepz_zonotopes: NULL centres / offsets");
+    CU(cudaSetDevice(ctx->device));
+    Compiled* c = nullptr;
+    int rc = compile_net(ctx, net, pp, n, &c);
+    if (rc) return rc;
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    DeepzInput in{};
+    in.kind = 1; in.n = n; in.N = N;
+    int p0max = 0;
+    if (N > 0) {
+        const void *dC, *dO, *dG;
+        if (dev_io) {
+            CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+            max_cols_kernel<<<std::min<long long>(1024, (N + 255) / 256), 256, 0, ctx->stream>>>((const long long*)col_off, N, ctx->d_err);
+            CU(cudaGetLastError());
+            ctx->launches++;
+            CU(cudaMemcpyAsync(&p0max, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            dC = C; dO = col_off; dG = G;
+        } else {
+            if (col_off[0] != 0) return fail(ctx, CLR_ERR_ARG, "col_off[0] must be 0");
+            for (int64_t i = 0; i < N; i++) {
+                int64_t p = col_off[i + 1] - col_off[i];
+                if (p < 0) return fail(ctx, CLR_ERR_ARG, "col_off must be non-decreasing (cell %lld)", (long long)i);
+                if (p > CLR_NCOL_MAX - 8) return fail(ctx, CLR_ERR_ARG, "cell %lld has %lld generators; at most %d supported", (long long)i, (long long)p, CLR_NCOL_MAX - 8);
+                p0max = std::max<int>(p0max, (int)p);
+            }
+            if (col_off[N] > 0 && !G) return fail(ctx, CLR_ERR_ARG, "clr_deepz_zonotopes: NULL generators");
+            if ((rc = stage_in(ctx, 0, C, sizeof(double) * (size_t)n * N, false, &dC))) return rc;
+            if ((rc = stage_in(ctx, 1, col_off, sizeof(int64_t) * (size_t)(N + 1), false, &dO))) return rc;
+            if ((rc = stage_in(ctx, 2, G, sizeof(double) * (size_t)n * col_off[N], false, &dG))) return rc;
+        }
+        in.C = (const double*)dC; in.col_off = (const long long*)dO; in.G = (const double*)dG;
+    }
+    return run_deepz(ctx, net, c, in, p0max, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags);
+}
+
+int32_t clr_deepz_fetch_zonotopes(clr_ctx* ctx, int32_t* out_ncols, double* out_c, double* out_G) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (ctx->keep_cells <= 0) return fail(ctx, CLR_ERR_STATE, "no kept zonotopes: run a DeepZ call with keep_cap > 0 first");
+    if (!out_ncols || !out_c || !out_G) return fail(ctx, CLR_ERR_ARG, "clr_deepz_fetch_zonotopes: NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t N = (size_t)ctx->keep_cells, m = (size_t)ctx->keep_m, cap = (size_t)ctx->keep_cap;
+    CU(cudaMemcpyAsync(out_ncols, ctx->d_keepN, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_c, ctx->d_keepC, sizeof(double) * m * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_G, ctx->d_keepG, sizeof(double) * m * cap * N, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // generators past ncols are unspecified on the device: zero them for the caller
+    for (size_t i = 0; i < N; i++) {
+        size_t k = (size_t)out_ncols[i];
+        if (k < cap) memset(out_G + (i * cap + k) * m, 0, sizeof(double) * (cap - k) * m);
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+template <int MAXW>
+int launch_points(clr_ctx* ctx, const PointNet& P, int nx, int64_t N, const double* X, double* U) {
+    size_t wbytes = sizeof(double) * (size_t)P.total_doubles;
+    int in_smem = wbytes <= (size_t)ctx->smem_optin - 1024;
+    size_t smem = in_smem ? wbytes : 0;
+    auto kern = forward_points_kernel<MAXW>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = in_smem ? std::max(1, std::min(8, (int)((size_t)ctx->smem_optin / (smem + 1024)))) : 8;
+    int grid = (int)std::min<int64_t>((N + 127) / 128, (int64_t)ctx->sms * per_sm);
+    kern<<<grid, 128, smem, ctx->stream>>>(P, nx, (long long)N, X, U, in_smem);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+template <int PLANT, int MAXW>
+int launch_rollout_t(clr_ctx* ctx, const PointNet& P, const RolloutArgs& A) {
+    size_t wbytes = sizeof(double) * (size_t)P.total_doubles;
+    int in_smem = wbytes <= (size_t)ctx->smem_optin - 1024;
+    size_t smem = in_smem ? wbytes : 0;
+    auto kern = rollout_kernel<PLANT, MAXW>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = in_smem ? std::max(1, std::min(8, (int)((size_t)ctx->smem_optin / (smem + 1024)))) : 8;
+    int grid = (int)std::min<int64_t>((A.N + 127) / 128, (int64_t)ctx->sms * per_sm);
+    kern<<<grid, 128, smem, ctx->stream>>>(P, A, in_smem);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+template <int PLANT>
+int launch_rollout_p(clr_ctx* ctx, int stored, const PointNet& P, const RolloutArgs& A) {
+    if (stored <= 8) return launch_rollout_t<PLANT, 8>(ctx, P, A);
+    if (stored <= 128) return launch_rollout_t<PLANT, 128>(ctx, P, A);
+    return launch_rollout_t<PLANT, 512>(ctx, P, A);
+}
+}  // namespace
+
+extern "C" {
+
+int32_t clr_forward_points(clr_ctx* ctx, const clr_net* net_c, const clr_prepost* pp, int32_t nx,
+                           int64_t N, const double* X, double* U, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    clr_net* net = const_cast<clr_net*>(net_c);
+    if (!net || nx < 1 || N < 0) return fail(ctx, CLR_ERR_ARG, "clr_forward_points: bad argument");
+    if (N > 0 && (!X || !U)) return fail(ctx, CLR_ERR_ARG, "clr_forward_points: NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    Compiled* c = nullptr;
+    int rc = compile_net(ctx, net, pp, nx, &c);
+    if (rc) return rc;
+    if (N == 0) return 0;
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    const int m = c->host.m_out;
+    const void* dX;
+    double* dU = U;
+    if ((rc = stage_in(ctx, 0, X, sizeof(double) * (size_t)nx * N, dev_io, &dX))) return rc;
+    if (!dev_io) {
+        if ((rc = ensure(ctx, &ctx->d_io[4], &ctx->io_bytes[4], sizeof(double) * (size_t)m * N))) return rc;
+        dU = (double*)ctx->d_io[4];
+    }
+    if (c->stored_width <= 8) rc = launch_points<8>(ctx, c->pnet, nx, N, (const double*)dX, dU);
+    else if (c->stored_width <= 128) rc = launch_points<128>(ctx, c->pnet, nx, N, (const double*)dX, dU);
+    else rc = launch_points<512>(ctx, c->pnet, nx, N, (const double*)dX, dU);
+    if (rc) return rc;
+    if (!dev_io) {
+        CU(cudaMemcpyAsync(U, dU, sizeof(double) * (size_t)m * N, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int32_t clr_rollout(clr_ctx* ctx, const clr_net* net_c, const clr_prepost* pp, int32_t plant,
+                    int32_t n_state, int32_t n_dist, int32_t n_ctrl, int64_t N, int32_t iters,
+                    const double* x0, const double* Wd, double t0, double tau, double T, int32_t alg,
+                    double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end,
+                    double* U, int32_t* naccept, int32_t* nreject, int32_t log_cap, int32_t* log_n,
+                    double* log_t, double* log_u, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    clr_net* net = const_cast<clr_net*>(net_c);
+    if (!net || N < 0 || iters < 0) return fail(ctx, CLR_ERR_ARG, "clr_rollout: bad argument");
+    int ns, nd, nc;
+    switch (plant) {
+        case CLR_PLANT_UNICYCLE: ns = 4; nd = 1; nc = 2; break;
+        case CLR_PLANT_TORA: ns = 4; nd = 0; nc = 1; break;
+        case CLR_PLANT_ACC: ns = 6; nd = 0; nc = 1; break;
+        case CLR_PLANT_INVPEND: ns = 2; nd = 0; nc = 1; break;
+        default: return fail(ctx, CLR_ERR_ARG, "unknown plant id %d", plant);
+    }
+    if (n_state != ns || n_dist != nd || n_ctrl != nc)
+        return fail(ctx, CLR_ERR_DIM, "plant %d has %d states, %d disturbances, %d controls; got %d, %d, %d", plant, ns, nd, nc, n_state, n_dist, n_ctrl);
+    if (alg != CLR_ALG_TSIT5 && alg != CLR_ALG_RK4) return fail(ctx, CLR_ERR_ARG, "unknown ODE algorithm %d", alg);
+    if (alg == CLR_ALG_RK4 && substeps < 1) return fail(ctx, CLR_ERR_ARG, "substeps must be >= 1");
+    if (log_cap < 0 || (log_cap > 0 && (!log_n || !log_t || !log_u))) return fail(ctx, CLR_ERR_ARG, "log buffers missing");
+    CU(cudaSetDevice(ctx->device));
+    Compiled* c = nullptr;
+    int rc = compile_net(ctx, net, pp, n_state, &c);
+    if (rc) return rc;
+    if (c->host.m_out != n_ctrl) return fail(ctx, CLR_ERR_DIM, "controller output dimension %d != n_ctrl %d", c->host.m_out, n_ctrl);
+    if (N == 0 || iters == 0) return 0;
+    if (!x0 || !X_end || !U || (nd > 0 && !Wd)) return fail(ctx, CLR_ERR_ARG, "clr_rollout: NULL buffer");
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    const size_t cells = (size_t)N * iters, ne = (size_t)ns + nd + nc;
+    RolloutArgs A{};
+    A.N = N; A.iters = iters; A.t0 = t0; A.tau = tau; A.T = T; A.alg = alg; A.abstol = abstol; A.reltol = reltol;
+    A.substeps = substeps; A.pow_mode = pow_mode; A.log_cap = log_cap; A.error = ctx->d_err;
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    const void *dx0, *dWd = nullptr;
+    if ((rc = stage_in(ctx, 0, x0, sizeof(double) * (size_t)ns * N, dev_io, &dx0))) return rc;
+    if (nd > 0 && (rc = stage_in(ctx, 1, Wd, sizeof(double) * nd * cells, dev_io, &dWd))) return rc;
+    A.x0 = (const double*)dx0; A.Wd = (const double*)dWd;
+    // outputs: one scratch allocation in blocking mode
+    unsigned char* base = nullptr;
+    size_t oX = 0, oU = 0, oA = 0, oR = 0, oLn = 0, oLt = 0, oLu = 0, total = 0;
+    auto take = [&](size_t bytes) { size_t o = total; total += (bytes + 255) & ~(size_t)255; return o; };
+    if (dev_io) {
+        A.X_end = X_end; A.U = U; A.naccept = naccept; A.nreject = nreject; A.log_n = log_n; A.log_t = log_t; A.log_u = log_u;
+    } else {
+        oX = take(sizeof(double) * ns * cells);
+        oU = take(sizeof(double) * nc * cells);
+        if (naccept) oA = take(sizeof(int) * cells);
+        if (nreject) oR = take(sizeof(int) * cells);
+        if (log_cap > 0) {
+            oLn = take(sizeof(int) * cells);
+            oLt = take(sizeof(double) * log_cap * cells);
+            oLu = take(sizeof(double) * ne * log_cap * cells);
+        }
+        if ((rc = ensure(ctx, &ctx->d_io[4], &ctx->io_bytes[4], total))) return rc;
+        base = (unsigned char*)ctx->d_io[4];
+        A.X_end = (double*)(base + oX); A.U = (double*)(base + oU);
+        A.naccept = naccept ? (int*)(base + oA) : nullptr;
+        A.nreject = nreject ? (int*)(base + oR) : nullptr;
+        if (log_cap > 0) { A.log_n = (int*)(base + oLn); A.log_t = (double*)(base + oLt); A.log_u = (double*)(base + oLu); }
+    }
+    switch (plant) {
+        case CLR_PLANT_UNICYCLE: rc = launch_rollout_p<CLR_PLANT_UNICYCLE>(ctx, c->stored_width, c->pnet, A); break;
+        case CLR_PLANT_TORA: rc = launch_rollout_p<CLR_PLANT_TORA>(ctx, c->stored_width, c->pnet, A); break;
+        case CLR_PLANT_ACC: rc = launch_rollout_p<CLR_PLANT_ACC>(ctx, c->stored_width, c->pnet, A); break;
+        default: rc = launch_rollout_p<CLR_PLANT_INVPEND>(ctx, c->stored_width, c->pnet, A); break;
+    }
+    if (rc) return rc;
+    if (!dev_io) {
+        CU(cudaMemcpyAsync(X_end, A.X_end, sizeof(double) * ns * cells, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(U, A.U, sizeof(double) * nc * cells, cudaMemcpyDeviceToHost, ctx->stream));
+        if (naccept) CU(cudaMemcpyAsync(naccept, A.naccept, sizeof(int) * cells, cudaMemcpyDeviceToHost, ctx->stream));
+        if (nreject) CU(cudaMemcpyAsync(nreject, A.nreject, sizeof(int) * cells, cudaMemcpyDeviceToHost, ctx->stream));
+        if (log_cap > 0) {
+            CU(cudaMemcpyAsync(log_n, A.log_n, sizeof(int) * cells, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(log_t, A.log_t, sizeof(double) * log_cap * cells, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(log_u, A.log_u, sizeof(double) * ne * log_cap * cells, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        int err = 0;
+        CU(cudaMemcpyAsync(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (err) return fail(ctx, err, "step log overflow: a period took more than log_cap - 1 = %d accepted steps", log_cap - 1);
+    }
+    return 0;
+}
+
+}  // extern "C"

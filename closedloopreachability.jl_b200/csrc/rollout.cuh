@@ -1,0 +1,463 @@
+// rollout.cuh -- batched closed-loop rollouts of simulate() and the pointwise controller.
+//
+// Replaces the period loop of the reference's simulate (src/simulate.jl:98-140): per trajectory and
+// control period the controller forward(x, network) (src/simulate.jl:101-106), the extended state
+// [x; w; u] (src/simulate.jl:117-124) and the ODE solve of _solve_ensemble
+// (ext/ClosedLoopReachabilityOrdinaryDiffEqExt.jl:28-45: Tsit5() with OrdinaryDiffEq's defaults).
+// One thread owns one trajectory for the whole horizon: the state stays in registers, the network
+// weights are staged once per CTA in shared memory and read as warp-wide broadcasts, and the only
+// HBM traffic is the state/disturbance read and the X_end / U write per period.
+#pragma once
+#include "common.cuh"
+
+#define RO_MAX_LAYERS (CLR_DEV_MAX_LAYERS)
+
+// Pointwise network: row-major copy of each W (dot products with the input) and the column-major one
+// (streaming a hidden neuron into the next layer's accumulators).
+struct PointNet {
+    int L;
+    int n_in, m_out;
+    int total_doubles;            // doubles needed to stage all weights in smem
+    int dims[RO_MAX_LAYERS + 1];
+    int act[RO_MAX_LAYERS];
+    const double* Wrm[RO_MAX_LAYERS];
+    const double* Wcm[RO_MAX_LAYERS];
+    const double* b[RO_MAX_LAYERS];
+    int off_rm[RO_MAX_LAYERS], off_cm[RO_MAX_LAYERS], off_b[RO_MAX_LAYERS];   // offsets in the smem image
+    const double* image;          // device: all weights in smem-image order
+};
+
+__device__ __forceinline__ double ro_act(int act, double s) {
+    switch (act) {
+        case CLR_ACT_RELU: return s > 0.0 ? s : 0.0;
+        case CLR_ACT_SIGMOID: return 1.0 / (1.0 + exp(-s));
+        case CLR_ACT_TANH: return tanh(s);
+        default: return s;
+    }
+}
+
+// Evaluate the network on one point.  Layers are processed in pairs: neuron i of layer l is computed
+// from the stored input vector and immediately streamed into the accumulators of layer l+1, so
+// only every other activation vector is materialised.  Summation order = ControllerFormats'
+// W*x + b (k ascending, bias last); products and sums are fused (fma).
+template <int MAXW>
+__device__ __forceinline__ void ro_mlp(const PointNet& net, const double* __restrict__ w, const double* xin,
+                                       double* uout) {
+    double va[MAXW], vb[MAXW];
+    if (MAXW <= 8) {
+#pragma unroll
+        for (int k = 0; k < MAXW; k++) va[k] = k < net.n_in ? xin[k] : 0.0;
+    } else {
+        for (int k = 0; k < net.n_in; k++) va[k] = xin[k];
+    }
+    int l = 0;
+    while (l < net.L) {
+        const int n = net.dims[l], m = net.dims[l + 1];
+        if (l + 1 < net.L) {
+            const int m2 = net.dims[l + 2];
+            const double* W1 = w + net.off_rm[l];
+            const double* b1 = w + net.off_b[l];
+            const double* W2 = w + net.off_cm[l + 1];
+            const double* b2 = w + net.off_b[l + 1];
+            const int a1 = net.act[l], a2 = net.act[l + 1];
+            if (MAXW <= 8) {
+#pragma unroll
+                for (int o = 0; o < MAXW; o++) vb[o] = 0.0;
+            } else {
+                for (int o = 0; o < m2; o++) vb[o] = 0.0;
+            }
+            for (int i = 0; i < m; i++) {
+                double s = 0.0;
+                if (MAXW <= 8) {
+#pragma unroll
+                    for (int k = 0; k < MAXW; k++) if (k < n) s = fma(W1[i * n + k], va[k], s);
+                } else {
+                    for (int k = 0; k < n; k++) s = fma(W1[i * n + k], va[k], s);
+                }
+                s += b1[i];
+                const double h = ro_act(a1, s);
+                if (MAXW <= 8) {
+#pragma unroll
+                    for (int o = 0; o < MAXW; o++) if (o < m2) vb[o] = fma(W2[i * m2 + o], h, vb[o]);
+                } else {
+                    for (int o = 0; o < m2; o++) vb[o] = fma(W2[i * m2 + o], h, vb[o]);
+                }
+            }
+            if (MAXW <= 8) {
+#pragma unroll
+                for (int o = 0; o < MAXW; o++) va[o] = o < m2 ? ro_act(a2, vb[o] + b2[o]) : 0.0;
+            } else {
+                for (int o = 0; o < m2; o++) va[o] = ro_act(a2, vb[o] + b2[o]);
+            }
+            l += 2;
+        } else {
+            const double* W1 = w + net.off_rm[l];
+            const double* b1 = w + net.off_b[l];
+            const int a1 = net.act[l];
+            if (MAXW <= 8) {
+#pragma unroll
+                for (int i = 0; i < MAXW; i++) {
+                    if (i < m) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int k = 0; k < MAXW; k++) if (k < n) s = fma(W1[i * n + k], va[k], s);
+                        vb[i] = ro_act(a1, s + b1[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < MAXW; i++) va[i] = i < m ? vb[i] : 0.0;
+            } else {
+                for (int i = 0; i < m; i++) {
+                    double s = 0.0;
+                    for (int k = 0; k < n; k++) s = fma(W1[i * n + k], va[k], s);
+                    vb[i] = ro_act(a1, s + b1[i]);
+                }
+                for (int i = 0; i < m; i++) va[i] = vb[i];
+            }
+            l += 1;
+        }
+    }
+    if (MAXW <= 8) {
+#pragma unroll
+        for (int k = 0; k < MAXW; k++) if (k < net.m_out) uout[k] = va[k];
+    } else {
+        for (int k = 0; k < net.m_out; k++) uout[k] = va[k];
+    }
+}
+
+// widths that must be materialised by ro_mlp (host uses the same rule to pick MAXW)
+__host__ __device__ inline int ro_stored_width(const int* dims, int L) {
+    int w = dims[0], l = 0;
+    while (l < L) {
+        if (l + 1 < L) { if (dims[l + 2] > w) w = dims[l + 2]; l += 2; }
+        else { if (dims[l + 1] > w) w = dims[l + 1]; l += 1; }
+    }
+    return w;
+}
+
+__device__ __forceinline__ const double* ro_stage_weights(const PointNet& net, double* sm, bool in_smem) {
+    if (!in_smem) return net.image;
+    for (int i = threadIdx.x; i < net.total_doubles; i += blockDim.x) sm[i] = __ldg(net.image + i);
+    __syncthreads();
+    return sm;
+}
+
+template <int MAXW>
+__global__ void __launch_bounds__(128)
+forward_points_kernel(PointNet net, int nx, long long N, const double* __restrict__ X, double* __restrict__ U,
+                      int in_smem) {
+    extern __shared__ __align__(16) double ro_sm[];
+    const double* w = ro_stage_weights(net, ro_sm, in_smem != 0);
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < N; j += (long long)gridDim.x * blockDim.x)
+        ro_mlp<MAXW>(net, w, X + j * nx, U + j * net.m_out);
+}
+
+// ---- plants on the extended state [x; w; u]; only the n_state leading entries have dynamics ---------
+template <int PLANT> struct PlantDims;
+template <> struct PlantDims<CLR_PLANT_UNICYCLE> { static constexpr int NS = 4, ND = 1, NC = 2; };
+template <> struct PlantDims<CLR_PLANT_TORA> { static constexpr int NS = 4, ND = 0, NC = 1; };
+template <> struct PlantDims<CLR_PLANT_ACC> { static constexpr int NS = 6, ND = 0, NC = 1; };
+template <> struct PlantDims<CLR_PLANT_INVPEND> { static constexpr int NS = 2, ND = 0, NC = 1; };
+
+// x: NS dynamic states, q: the constant tail [w; u]
+template <int PLANT>
+__device__ __forceinline__ void plant_rhs(const double* x, const double* q, double* dx) {
+    if (PLANT == CLR_PLANT_UNICYCLE) {            // models/Unicycle/Unicycle.jl:36-47
+        dx[0] = x[3] * cos(x[2]);
+        dx[1] = x[3] * sin(x[2]);
+        dx[2] = q[2];
+        dx[3] = q[1] + q[0];
+    } else if (PLANT == CLR_PLANT_TORA) {         // models/TORA/TORA.jl:46-55
+        dx[0] = x[1];
+        dx[1] = -x[0] + (0.1 * sin(x[2]));
+        dx[2] = x[3];
+        dx[3] = q[0];
+    } else if (PLANT == CLR_PLANT_ACC) {          // models/ACC/ACC.jl:41-60
+        dx[0] = x[1];
+        dx[1] = x[2];
+        dx[2] = 2 * (-2.0 - x[2]) - 0.0001 * (x[1] * x[1]);
+        dx[3] = x[4];
+        dx[4] = x[5];
+        dx[5] = 2 * (q[0] - x[5]) - 0.0001 * (x[4] * x[4]);
+    } else {                                      // models/InvertedPendulum/InvertedPendulum.jl:44-51
+        dx[0] = x[1];
+        dx[1] = 2.0 * sin(x[0]) + 8.0 * (q[0] - 0.0 * x[1]);
+    }
+}
+
+// DiffEqBase fastpow (Float32 round trip), bit-identical to the CPU restatement
+__device__ __forceinline__ float ro_fastlog2f(float x) {
+    const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+    unsigned ux1i = __float_as_uint(x);
+    unsigned ex = (ux1i & 0x7F800000u) >> 23;
+    unsigned greater = ux1i & 0x00400000u;
+    float signif, fexp;
+    if (greater) { signif = __uint_as_float((ux1i & 0x007FFFFFu) | 0x3f000000u); fexp = __fsub_rn((float)ex, 126.0f); }
+    else { signif = __uint_as_float((ux1i & 0x007FFFFFu) | 0x3f800000u); fexp = __fsub_rn((float)ex, 127.0f); }
+    signif = __fsub_rn(signif, 1.0f);
+    float num = __fmul_rn(signif, __fadd_rn(__fmul_rn(a, signif), b));
+    return __fadd_rn(fexp, __fdiv_rn(num, __fadd_rn(signif, c)));
+}
+__device__ __forceinline__ float ro_fastpow2f(float x) {
+    float offset = x < 0 ? 1.0f : 0.0f;
+    float clipp = x < -126.0f ? -126.0f : x;
+    int w = (int)clipp;
+    float z = __fadd_rn(__fsub_rn(clipp, (float)w), offset);
+    float t = __fadd_rn(clipp, 121.2740575f);
+    t = __fadd_rn(t, __fdiv_rn(27.7280233f, __fsub_rn(4.84252568f, z)));
+    t = __fsub_rn(t, __fmul_rn(1.49012907f, z));
+    float v = __fmul_rn((float)(1 << 23), t);
+    return __uint_as_float((unsigned)v);
+}
+__device__ __forceinline__ double ro_pow(double x, double y, int mode) {
+    if (mode == 0) return pow(x, y);
+    if (x == 0.0) return 0.0;
+    return (double)ro_fastpow2f(__fmul_rn((float)y, ro_fastlog2f((float)x)));
+}
+
+struct RolloutArgs {
+    long long N;
+    int iters;
+    const double* x0;      // NS x N
+    const double* Wd;      // ND x N x iters or nullptr
+    double t0, tau, T;
+    int alg;
+    double abstol, reltol;
+    int substeps, pow_mode;
+    double* X_end;         // NS x N x iters
+    double* U;             // NC x N x iters
+    int* naccept;          // N x iters or nullptr
+    int* nreject;
+    int log_cap;
+    int* log_n;
+    double* log_t;
+    double* log_u;
+    int* error;            // device flag: CLR_ERR_CAPACITY when a step log overflows
+};
+
+#define TS_A21 0.161
+#define TS_A31 -0.008480655492356989
+#define TS_A32 0.335480655492357
+#define TS_A41 2.8971530571054935
+#define TS_A42 -6.359448489975075
+#define TS_A43 4.3622954328695815
+#define TS_A51 5.325864828439257
+#define TS_A52 -11.748883564062828
+#define TS_A53 7.4955393428898365
+#define TS_A54 -0.09249506636175525
+#define TS_A61 5.86145544294642
+#define TS_A62 -12.92096931784711
+#define TS_A63 8.159367898576159
+#define TS_A64 -0.071584973281401
+#define TS_A65 -0.028269050394068383
+#define TS_A71 0.09646076681806523
+#define TS_A72 0.01
+#define TS_A73 0.4798896504144996
+#define TS_A74 1.379008574103742
+#define TS_A75 -3.290069515436081
+#define TS_A76 2.324710524099774
+#define TS_BT1 -0.00178001105222577714
+#define TS_BT2 -0.0008164344596567469
+#define TS_BT3 0.007880878010261995
+#define TS_BT4 -0.1447110071732629
+#define TS_BT5 0.5823571654525552
+#define TS_BT6 -0.45808210592918697
+#define TS_BT7 0.015151515151515152
+
+__device__ __forceinline__ double ro_eps_of(double x) {
+    x = fabs(x);
+    return __longlong_as_double(__double_as_longlong(x) + 1) - x;
+}
+
+// One ODE.solve(prob, Tsit5()) over [t0, t1] on the NS dynamic states (tail q constant).
+// Mirrors OrdinaryDiffEq v6: initdt (order 5), PI controller (beta1 7/50, beta2 2/25, gamma 9/10,
+// qmin 1/5, qmax 10), error norm over the whole extended state (the constant tail contributes 0).
+template <int PLANT>
+__device__ __forceinline__ void ro_tsit5(double* x, const double* q, double t0, double t1, const RolloutArgs& A,
+                                         long long cell, int& nacc, int& nrej) {
+    constexpr int NS = PlantDims<PLANT>::NS, NQ = PlantDims<PLANT>::ND + PlantDims<PLANT>::NC, NE = NS + NQ;
+    const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 9.0 / 10.0, qmin = 1.0 / 5.0, qmax = 10.0;
+    const double abstol = A.abstol, reltol = A.reltol;
+    double k1[NS], k2[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS], tmp[NS], un[NS];
+    double t = t0;
+    const double dtmax = t1 - t0;
+    int nlog = 0;
+    const int log_cap = A.log_cap;
+    if (log_cap > 0) {
+        A.log_t[cell * log_cap] = t;
+        double* lu = A.log_u + (size_t)cell * log_cap * NE;
+#pragma unroll
+        for (int i = 0; i < NS; i++) lu[i] = x[i];
+#pragma unroll
+        for (int i = 0; i < NQ; i++) lu[NS + i] = q[i];
+        nlog = 1;
+    }
+    plant_rhs<PLANT>(x, q, k1);
+    double dt;
+    {   // ode_determine_initdt
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            double sk = abstol + fabs(x[i]) * reltol;
+            double a = x[i] / sk, b = k1[i] / sk;
+            s0 += a * a; s1 += b * b;
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; i++) {
+            double sk = abstol + fabs(q[i]) * reltol;
+            double a = q[i] / sk;
+            s0 += a * a; s1 += 0.0;
+        }
+        double d0 = sqrt(s0 / NE), d1 = sqrt(s1 / NE);
+        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (d0 / d1) / 100;
+        if (dt0 > dtmax) dt0 = dtmax;
+        if (dt0 < 10 * 2.220446049250313e-16) {
+            dt = 1e-6;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NS; i++) un[i] = x[i] + dt0 * k1[i];
+            plant_rhs<PLANT>(un, q, k2);
+            double s2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                double sk = abstol + fabs(x[i]) * reltol;
+                double a = (k2[i] - k1[i]) / sk;
+                s2 += a * a;
+            }
+            double d2 = sqrt(s2 / NE) / dt0;
+            double md = d1 > d2 ? d1 : d2;
+            double dt1 = md <= 1e-15 ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2 + log10(md)) / 5);
+            dt = fmin(fmin(100 * dt0, dt1), dtmax);
+        }
+    }
+    double qold = 1e-4;
+    int guard = 0;
+    while (t < t1 && guard++ < 1000000) {
+        if (dt > t1 - t) dt = t1 - t;
+#pragma unroll
+        for (int i = 0; i < NS; i++) tmp[i] = x[i] + dt * (TS_A21 * k1[i]);
+        plant_rhs<PLANT>(tmp, q, k2);
+#pragma unroll
+        for (int i = 0; i < NS; i++) tmp[i] = x[i] + dt * (TS_A31 * k1[i] + TS_A32 * k2[i]);
+        plant_rhs<PLANT>(tmp, q, k3);
+#pragma unroll
+        for (int i = 0; i < NS; i++) tmp[i] = x[i] + dt * (TS_A41 * k1[i] + TS_A42 * k2[i] + TS_A43 * k3[i]);
+        plant_rhs<PLANT>(tmp, q, k4);
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            tmp[i] = x[i] + dt * (TS_A51 * k1[i] + TS_A52 * k2[i] + TS_A53 * k3[i] + TS_A54 * k4[i]);
+        plant_rhs<PLANT>(tmp, q, k5);
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            tmp[i] = x[i] + dt * (TS_A61 * k1[i] + TS_A62 * k2[i] + TS_A63 * k3[i] + TS_A64 * k4[i] + TS_A65 * k5[i]);
+        plant_rhs<PLANT>(tmp, q, k6);
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            un[i] = x[i] + dt * (TS_A71 * k1[i] + TS_A72 * k2[i] + TS_A73 * k3[i] + TS_A74 * k4[i] + TS_A75 * k5[i] +
+                                 TS_A76 * k6[i]);
+        plant_rhs<PLANT>(un, q, k7);
+        double se = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            double e = TS_BT1 * k1[i] + TS_BT2 * k2[i] + TS_BT3 * k3[i] + TS_BT4 * k4[i] + TS_BT5 * k5[i] +
+                       TS_BT6 * k6[i] + TS_BT7 * k7[i];
+            e = dt * e;
+            double r = e / (abstol + fmax(fabs(x[i]), fabs(un[i])) * reltol);
+            se += r * r;
+        }
+        double EEst = sqrt(se / NE);
+        double qq, q11 = 0.0;
+        if (EEst == 0.0) {
+            qq = 1.0 / qmax;
+        } else {
+            q11 = ro_pow(EEst, beta1, A.pow_mode);
+            qq = q11 / ro_pow(qold, beta2, A.pow_mode);
+            qq = fmax(1.0 / qmax, fmin(1.0 / qmin, qq / gamma));
+        }
+        if (EEst <= 1.0) {
+            nacc++;
+            qold = fmax(EEst, 1e-4);
+            double dtnew = dt / qq;
+            double ttmp = t + dt;
+            if (fabs(ttmp - t1) < 100 * ro_eps_of(fmax(t, t1))) ttmp = t1;
+            t = ttmp;
+#pragma unroll
+            for (int i = 0; i < NS; i++) { x[i] = un[i]; k1[i] = k7[i]; }
+            dt = fmin(dtnew, dtmax);
+            if (log_cap > 0) {
+                if (nlog < log_cap) {
+                    A.log_t[cell * log_cap + nlog] = t;
+                    double* lu = A.log_u + ((size_t)cell * log_cap + nlog) * NE;
+#pragma unroll
+                    for (int i = 0; i < NS; i++) lu[i] = x[i];
+#pragma unroll
+                    for (int i = 0; i < NQ; i++) lu[NS + i] = q[i];
+                    nlog++;
+                } else {
+                    atomicCAS(A.error, 0, (int)CLR_ERR_CAPACITY);
+                }
+            }
+        } else {
+            nrej++;
+            dt = dt / fmin(1.0 / qmin, q11 / gamma);
+        }
+    }
+    if (log_cap > 0) A.log_n[cell] = nlog;
+}
+
+template <int PLANT>
+__device__ __forceinline__ void ro_rk4(double* x, const double* q, double t0, double t1, int substeps) {
+    constexpr int NS = PlantDims<PLANT>::NS;
+    double k1[NS], k2[NS], k3[NS], k4[NS], tmp[NS];
+    const double dt = (t1 - t0) / substeps;
+    for (int s = 0; s < substeps; s++) {
+        plant_rhs<PLANT>(x, q, k1);
+#pragma unroll
+        for (int i = 0; i < NS; i++) tmp[i] = x[i] + (dt / 2) * k1[i];
+        plant_rhs<PLANT>(tmp, q, k2);
+#pragma unroll
+        for (int i = 0; i < NS; i++) tmp[i] = x[i] + (dt / 2) * k2[i];
+        plant_rhs<PLANT>(tmp, q, k3);
+#pragma unroll
+        for (int i = 0; i < NS; i++) tmp[i] = x[i] + dt * k3[i];
+        plant_rhs<PLANT>(tmp, q, k4);
+#pragma unroll
+        for (int i = 0; i < NS; i++) x[i] = x[i] + (dt / 6) * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+    }
+}
+
+template <int PLANT, int MAXW>
+__global__ void __launch_bounds__(128)
+rollout_kernel(PointNet net, RolloutArgs A, int in_smem) {
+    constexpr int NS = PlantDims<PLANT>::NS, ND = PlantDims<PLANT>::ND, NC = PlantDims<PLANT>::NC;
+    extern __shared__ __align__(16) double ro_sm[];
+    const double* w = ro_stage_weights(net, ro_sm, in_smem != 0);
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < A.N; j += (long long)gridDim.x * blockDim.x) {
+        double x[NS], q[ND + NC];
+#pragma unroll
+        for (int i = 0; i < NS; i++) x[i] = A.x0[j * NS + i];
+        double t = A.t0;
+        for (int it = 0; it < A.iters; it++) {
+            double xin[8], u[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) xin[i] = i < NS ? x[i] : 0.0;
+            ro_mlp<MAXW>(net, w, xin, u);
+            const long long cell = (long long)it * A.N + j;
+#pragma unroll
+            for (int i = 0; i < NC; i++) A.U[cell * NC + i] = u[i];
+#pragma unroll
+            for (int i = 0; i < ND; i++) q[i] = A.Wd[cell * ND + i];
+#pragma unroll
+            for (int i = 0; i < NC; i++) q[ND + i] = u[i];
+            const double t1 = it < A.iters - 1 ? t + A.tau : A.T;
+            int nacc = 0, nrej = 0;
+            if (A.alg == CLR_ALG_TSIT5) ro_tsit5<PLANT>(x, q, t, t1, A, cell, nacc, nrej);
+            else { ro_rk4<PLANT>(x, q, t, t1, A.substeps); nacc = A.substeps; }
+            if (A.naccept) A.naccept[cell] = nacc;
+            if (A.nreject) A.nreject[cell] = nrej;
+#pragma unroll
+            for (int i = 0; i < NS; i++) A.X_end[cell * NS + i] = x[i];
+            t = t1;
+        }
+    }
+}

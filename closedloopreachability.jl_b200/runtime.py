@@ -1,0 +1,320 @@
+"""NumPy-facing wrapper of the C ABI (include/clr_b200.h): one ``Context`` per CUDA device.
+
+Array conventions: a batch of vectors is a C-ordered ``(N, dim)`` array, which is the
+``dim x N`` column-major layout the C ABI (and Julia) uses.  All compute happens in
+libclr_b200.so; nothing here falls back to NumPy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .network import ACT_IDS, FeedforwardNetwork
+
+PLANTS = {"Unicycle": 1, "TORA": 2, "ACC": 3, "InvertedPendulum": 4}
+PLANT_DIMS = {1: (4, 1, 2), 2: (4, 0, 1), 3: (6, 0, 1), 4: (2, 0, 1)}   # n_state, n_dist, n_ctrl
+FLAG_DEVICE_IO = 1
+FLAG_NO_STATS = 2
+ERR_ARG, ERR_CAPACITY, ERR_DIM, ERR_CUDA, ERR_ALLOC, ERR_STATE = -1, -2, -3, -4, -5, -6
+
+
+class ClrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libclr_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ClrArgumentError(ClrError, ValueError):
+    """CLR_ERR_ARG / CLR_ERR_DIM -- what the Julia host turns into ArgumentError (src/solve.jl:88-99, :130-134)."""
+
+
+def _raise(code, msg):
+    if code in (ERR_ARG, ERR_DIM):
+        raise ClrArgumentError(code, msg)
+    raise ClrError(code, msg)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):            # torch tensor (device or pinned host memory)
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class PrePostArg:
+    """Builds a clr_prepost; ``pre = (A, d)`` (affine x -> A x + d) or None;
+    ``post = None | ("shift", s) | ("scale", a) | ("matrix", M) | ("project", dims0)``
+    mirroring the reference's post-processing types (src/problem.jl:5-58)."""
+
+    def __init__(self, pre=None, post=None):
+        self.keep = []
+        s = _lib.PrePost()
+        if pre is not None:
+            A, d = pre
+            A = np.asfortranarray(A, dtype=np.float64)
+            d = np.ascontiguousarray(d, dtype=np.float64)
+            if A.ndim != 2 or d.shape != (A.shape[0],):
+                raise ClrArgumentError(ERR_DIM, "preprocessing must be (A (r, n), d (r,))")
+            self.keep += [A, d]
+            s.pre_rows, s.preA, s.preb = A.shape[0], A.ctypes.data, d.ctypes.data
+        if post is not None:
+            kind, val = post
+            if kind == "shift":
+                v = np.array([val], dtype=np.float64)
+                self.keep.append(v)
+                s.post_kind, s.postb = 1, v.ctypes.data
+            elif kind == "scale":
+                v = np.array([val], dtype=np.float64)
+                self.keep.append(v)
+                s.post_kind, s.postA = 2, v.ctypes.data
+            elif kind == "matrix":
+                M = np.asfortranarray(val, dtype=np.float64)
+                self.keep.append(M)
+                s.post_kind, s.post_rows, s.postA = 3, M.shape[0], M.ctypes.data
+            elif kind == "project":
+                d = np.ascontiguousarray(val, dtype=np.int32)
+                self.keep.append(d)
+                s.post_kind, s.post_rows, s.post_dims = 4, len(d), d.ctypes.data
+            else:
+                raise ClrArgumentError(ERR_ARG, f"unknown postprocessing {kind!r}")
+        self.s = s
+
+    def out_dim(self, net_out):
+        return self.s.post_rows if self.s.post_kind in (3, 4) else net_out
+
+
+def stats_dict(st, L):
+    return {"n_cells": st.n_cells, "sum_p_in": list(st.sum_p_in)[:L],
+            "sum_unstable": list(st.sum_unstable)[:L], "near_threshold": st.near_threshold,
+            "max_p_out": st.max_p_out, "flops": st.flops}
+
+
+class DeviceNetwork:
+    """A FeedforwardNetwork uploaded to one Context (clr_net)."""
+
+    def __init__(self, ctx: "Context", net: FeedforwardNetwork):
+        self.ctx = ctx
+        self.net = net
+        self.dims = list(net.dims)
+        L = len(net.layers)
+        self._W = [np.asfortranarray(l.weights, dtype=np.float64) for l in net.layers]
+        self._b = [np.ascontiguousarray(l.bias, dtype=np.float64) for l in net.layers]
+        dims = (C.c_int32 * (L + 1))(*self.dims)
+        act = (C.c_int32 * L)(*[ACT_IDS[l.activation] for l in net.layers])
+        Wp = (C.c_void_p * L)(*[w.ctypes.data for w in self._W])
+        bp = (C.c_void_p * L)(*[b.ctypes.data for b in self._b])
+        h = C.c_void_p()
+        ctx._check(ctx.L.clr_net_upload(ctx.h, L, dims, act, Wp, bp, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx.L.clr_net_free(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+
+class Context:
+    """clr_ctx: bound to one CUDA device; owns a stream and all device scratch memory."""
+
+    def __init__(self, device: int = 0):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        rc = self.L.clr_create(device, C.byref(h))
+        if rc != 0:
+            _raise(rc, (self.L.clr_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.clr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            _raise(rc, (self.L.clr_last_error(self.h) or b"").decode())
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return int(self.L.clr_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._check(self.L.clr_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.clr_launch_count(self.h))
+
+    def set_tile_cells(self, cells: int):
+        self._check(self.L.clr_set_tile_cells(self.h, int(cells)))
+
+    def upload(self, net: FeedforwardNetwork) -> DeviceNetwork:
+        return DeviceNetwork(self, net)
+
+    # ---- DeepZ ------------------------------------------------------------------------------------
+    def deepz_boxgrid(self, dnet: DeviceNetwork, partition, centers, radii, cell_begin=0, cell_count=None,
+                      pre=None, post=None, hull=False, stats=True, keep_cap=0, boxes=True):
+        """All cells [cell_begin, cell_begin+cell_count) of a box split through controller_forward.
+
+        ``centers`` / ``radii``: per-dimension tables (lists of 1-D arrays; ``radii`` per block).
+        Returns ``{"lo", "hi"}`` of shape (cell_count, m) plus optional ``hull_lo/hull_hi``, ``stats``.
+        """
+        part = np.ascontiguousarray(partition, dtype=np.int32)
+        n = len(part)
+        total = int(np.prod(part.astype(object))) if n else 0
+        if cell_count is None:
+            cell_count = total - cell_begin
+        cc = np.ascontiguousarray(np.concatenate([np.atleast_1d(c) for c in centers]), dtype=np.float64)
+        rr = np.ascontiguousarray(np.concatenate([np.atleast_1d(r) for r in radii]), dtype=np.float64)
+        if n and (len(cc) != int(part.sum()) or len(rr) != int(part.sum())):
+            raise ClrArgumentError(ERR_DIM, "centre / radius tables do not match the partition")
+        pp = PrePostArg(pre, post)
+        m = pp.out_dim(dnet.dims[-1])
+        cnt = max(int(cell_count), 0)
+        lo = np.empty((cnt, m)) if boxes else None
+        hi = np.empty((cnt, m)) if boxes else None
+        hl = np.empty(m) if hull else None
+        hh = np.empty(m) if hull else None
+        st = _lib.Stats() if stats else None
+        rc = self.L.clr_deepz_boxgrid(self.h, dnet.h, n, _ptr(part), _ptr(cc), _ptr(rr), int(cell_begin),
+                                      int(cell_count), C.byref(pp.s), _ptr(lo), _ptr(hi), _ptr(hl), _ptr(hh),
+                                      C.byref(st) if stats else None, int(keep_cap), 0 if stats else FLAG_NO_STATS)
+        self._check(rc)
+        out = {"lo": lo, "hi": hi}
+        if hull:
+            out.update(hull_lo=hl, hull_hi=hh)
+        if stats:
+            out["stats"] = stats_dict(st, len(dnet.net.layers))
+        if keep_cap:
+            out.update(self.fetch_zonotopes(cnt, m, keep_cap))
+        return out
+
+    def deepz_zonotopes(self, dnet: DeviceNetwork, Cc, col_off, G, pre=None, post=None, hull=False, stats=True,
+                        keep_cap=0, boxes=True):
+        """Cc: (N, n) centres; G: (total_cols, n), row j = generator j; col_off: (N+1,) int64."""
+        Cc = np.ascontiguousarray(Cc, dtype=np.float64)
+        if Cc.ndim != 2:
+            raise ClrArgumentError(ERR_DIM, "centres must be (N, n)")
+        N, n = Cc.shape
+        G = np.ascontiguousarray(G, dtype=np.float64).reshape(-1, n)
+        col_off = np.ascontiguousarray(col_off, dtype=np.int64)
+        if col_off.shape != (N + 1,) or (N > 0 and col_off[-1] != G.shape[0]):
+            raise ClrArgumentError(ERR_DIM, "col_off must have N+1 entries and end at the number of generators")
+        pp = PrePostArg(pre, post)
+        m = pp.out_dim(dnet.dims[-1])
+        lo = np.empty((N, m)) if boxes else None
+        hi = np.empty((N, m)) if boxes else None
+        hl = np.empty(m) if hull else None
+        hh = np.empty(m) if hull else None
+        st = _lib.Stats() if stats else None
+        rc = self.L.clr_deepz_zonotopes(self.h, dnet.h, n, N, _ptr(Cc), _ptr(col_off), _ptr(G), C.byref(pp.s),
+                                        _ptr(lo), _ptr(hi), _ptr(hl), _ptr(hh), C.byref(st) if stats else None,
+                                        int(keep_cap), 0 if stats else FLAG_NO_STATS)
+        self._check(rc)
+        out = {"lo": lo, "hi": hi}
+        if hull:
+            out.update(hull_lo=hl, hull_hi=hh)
+        if stats:
+            out["stats"] = stats_dict(st, len(dnet.net.layers))
+        if keep_cap:
+            out.update(self.fetch_zonotopes(N, m, keep_cap))
+        return out
+
+    def fetch_zonotopes(self, N, m, keep_cap):
+        nc = np.zeros(N, dtype=np.int32)
+        c = np.zeros((N, m))
+        G = np.zeros((N, keep_cap, m))
+        if N > 0:
+            self._check(self.L.clr_deepz_fetch_zonotopes(self.h, _ptr(nc), _ptr(c), _ptr(G)))
+        return {"ncols": nc, "c": c, "G": G}
+
+    # device-resident variant: every data pointer is a device pointer / torch CUDA tensor
+    def deepz_boxgrid_dev(self, dnet, n, d_partition_host, d_centers, d_radii, cell_begin, cell_count, pp: PrePostArg,
+                          d_lo, d_hi, d_hull_lo=None, d_hull_hi=None, stats=None, keep_cap=0):
+        part = np.ascontiguousarray(d_partition_host, dtype=np.int32)
+        flags = FLAG_DEVICE_IO | (0 if stats is not None else FLAG_NO_STATS)
+        rc = self.L.clr_deepz_boxgrid(self.h, dnet.h, n, _ptr(part), _ptr(d_centers), _ptr(d_radii),
+                                      int(cell_begin), int(cell_count), C.byref(pp.s), _ptr(d_lo), _ptr(d_hi),
+                                      _ptr(d_hull_lo), _ptr(d_hull_hi), C.byref(stats) if stats is not None else None,
+                                      int(keep_cap), flags)
+        self._check(rc)
+
+    def deepz_zonotopes_dev(self, dnet, n, N, d_C, d_col_off, d_G, pp: PrePostArg, d_lo, d_hi, d_hull_lo=None,
+                            d_hull_hi=None, stats=None, keep_cap=0):
+        flags = FLAG_DEVICE_IO | (0 if stats is not None else FLAG_NO_STATS)
+        rc = self.L.clr_deepz_zonotopes(self.h, dnet.h, n, int(N), _ptr(d_C), _ptr(d_col_off), _ptr(d_G),
+                                        C.byref(pp.s), _ptr(d_lo), _ptr(d_hi), _ptr(d_hull_lo), _ptr(d_hull_hi),
+                                        C.byref(stats) if stats is not None else None, int(keep_cap), flags)
+        self._check(rc)
+
+    # ---- pointwise controller / rollouts ---------------------------------------------------------------
+    def forward_points(self, dnet: DeviceNetwork, X, pre=None, post=None):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ClrArgumentError(ERR_DIM, "X must be (N, n)")
+        N, nx = X.shape
+        pp = PrePostArg(pre, post)
+        U = np.empty((N, pp.out_dim(dnet.dims[-1])))
+        self._check(self.L.clr_forward_points(self.h, dnet.h, C.byref(pp.s), nx, N, _ptr(X), _ptr(U), 0))
+        return U
+
+    def rollout(self, dnet: DeviceNetwork, plant, x0, Wd, t0, tau, T, iters, alg="Tsit5", abstol=1e-6, reltol=1e-3,
+                substeps=4, pow_mode=1, pre=None, post=None, log_cap=0, counts=True):
+        """x0: (N, n_state); Wd: (iters, N, n_dist) or None.  Returns X_end (iters, N, n_state), U (iters, N, n_ctrl)."""
+        pid = PLANTS[plant] if isinstance(plant, str) else int(plant)
+        ns, nd, nc = PLANT_DIMS.get(pid, (0, 0, 0))
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        if x0.ndim != 2:
+            raise ClrArgumentError(ERR_DIM, "x0 must be (N, n_state)")
+        N = x0.shape[0]
+        if nd:
+            Wd = np.ascontiguousarray(Wd, dtype=np.float64).reshape(iters, N, nd)
+        pp = PrePostArg(pre, post)
+        X_end = np.empty((iters, N, ns))
+        U = np.empty((iters, N, nc))
+        na = np.zeros((iters, N), dtype=np.int32) if counts else None
+        nr = np.zeros((iters, N), dtype=np.int32) if counts else None
+        ln = lt = lu = None
+        if log_cap:
+            ln = np.zeros((iters, N), dtype=np.int32)
+            lt = np.zeros((iters, N, log_cap))
+            lu = np.zeros((iters, N, log_cap, ns + nd + nc))
+        rc = self.L.clr_rollout(self.h, dnet.h, C.byref(pp.s), pid, x0.shape[1], nd, nc, N, int(iters), _ptr(x0),
+                                _ptr(Wd) if nd else None, float(t0), float(tau), float(T),
+                                0 if alg == "Tsit5" else 1, float(abstol), float(reltol), int(substeps),
+                                int(pow_mode), _ptr(X_end), _ptr(U), _ptr(na), _ptr(nr), int(log_cap), _ptr(ln),
+                                _ptr(lt), _ptr(lu), 0)
+        self._check(rc)
+        out = {"X_end": X_end, "U": U}
+        if counts:
+            out.update(naccept=na, nreject=nr)
+        if log_cap:
+            out.update(log_n=ln, log_t=lt, log_u=lu)
+        return out
+
+    def rollout_dev(self, dnet, plant, N, iters, d_x0, d_Wd, t0, tau, T, alg, abstol, reltol, substeps, pow_mode,
+                    pp: PrePostArg, d_X_end, d_U, d_naccept=None, d_nreject=None):
+        pid = PLANTS[plant] if isinstance(plant, str) else int(plant)
+        ns, nd, nc = PLANT_DIMS[pid]
+        rc = self.L.clr_rollout(self.h, dnet.h, C.byref(pp.s), pid, ns, nd, nc, int(N), int(iters), _ptr(d_x0),
+                                _ptr(d_Wd), float(t0), float(tau), float(T), 0 if alg == "Tsit5" else 1,
+                                float(abstol), float(reltol), int(substeps), int(pow_mode), _ptr(d_X_end), _ptr(d_U),
+                                _ptr(d_naccept), _ptr(d_nreject), 0, None, None, None, FLAG_DEVICE_IO)
+        self._check(rc)

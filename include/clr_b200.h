@@ -1,0 +1,178 @@
+/*
+ * clr_b200.h -- C ABI of libclr_b200.so: the B200 (sm_100a) hot path of ClosedLoopReachability.jl.
+ *
+ * This is the drop-in boundary.  The Julia host files (src/solve.jl, src/splitters.jl,
+ * src/simulate.jl of the reference) `ccall` these entry points; the Python mirror in
+ * closedloopreachability.jl_b200/ binds the same symbols with ctypes (INTEGRATION.md shows both).
+ *
+ * Conventions
+ *  - every matrix is Float64 column-major (Julia native); a batch of vectors is stored
+ *    "dim x N" column-major, i.e. unit (cell / trajectory) j owns the contiguous slice [j*dim, (j+1)*dim);
+ *  - the caller owns every buffer it passes; the library owns all device memory inside clr_ctx;
+ *  - every function returns 0 on success and a negative clr_status on error; the message is
+ *    available from clr_last_error(); no C++ exception crosses the boundary;
+ *  - a clr_ctx is bound to ONE CUDA device and is not thread-safe (one ctx per host task);
+ *    calls block the calling thread unless CLR_FLAG_DEVICE_IO is set;
+ *  - there is no CPU fallback: without a CUDA device clr_create fails with CLR_ERR_CUDA.
+ *
+ * Reference interface replaced by each entry point (paths relative to the reference repo):
+ *   clr_net_upload            FeedforwardNetwork / DenseLayerOp as used by src/solve.jl:212, src/simulate.jl:104
+ *   clr_deepz_boxgrid         the cell loops of _solve, src/solve.jl:153-166 and :187-195, over
+ *                             apply(BoxSplitter, X0) (src/splitters.jl:20-28), each cell going through
+ *                             controller_forward (src/solve.jl:210-218) with algorithm_controller = DeepZ()
+ *   clr_deepz_zonotopes       same loops for arbitrary zonotope cells (k > 1, ZonotopeSplitter cells,
+ *                             models/VerticalCAS/VerticalCAS.jl:122 direct forward(Y, net, DeepZ()) calls)
+ *   clr_deepz_fetch_zonotopes the output set U of controller_forward (src/solve.jl:213) when the caller
+ *                             needs more than its box (TaylorModelReconstructor(box=false), src/setops.jl:84-107)
+ *   clr_forward_points        forward(x, network) + pre/post-processing, src/simulate.jl:101-106
+ *   clr_rollout               the period loop of simulate (src/simulate.jl:98-140) incl. _solve_ensemble
+ *                             (ext/ClosedLoopReachabilityOrdinaryDiffEqExt.jl:28-45: Tsit5 ensemble)
+ */
+#ifndef CLR_B200_H
+#define CLR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLR_MAX_LAYERS 32
+
+typedef enum {
+    CLR_OK = 0,
+    CLR_ERR_ARG = -1,        /* invalid argument (Julia side: ArgumentError) */
+    CLR_ERR_CAPACITY = -2,   /* keep_cap / log_cap too small for a result */
+    CLR_ERR_DIM = -3,        /* dimension mismatch (Julia side: ArgumentError, src/solve.jl:130-134) */
+    CLR_ERR_CUDA = -4,       /* CUDA runtime error or no device */
+    CLR_ERR_ALLOC = -5,
+    CLR_ERR_STATE = -6       /* call order (e.g. fetch before a keep run) */
+} clr_status;
+
+/* activations (ControllerFormats names) */
+enum { CLR_ACT_ID = 0, CLR_ACT_RELU = 1, CLR_ACT_SIGMOID = 2, CLR_ACT_TANH = 3 };
+/* post-processing kinds (src/problem.jl:5-58) */
+enum { CLR_POST_NONE = 0, CLR_POST_SHIFT = 1, CLR_POST_SCALE = 2, CLR_POST_MATRIX = 3, CLR_POST_PROJECT = 4 };
+/* built-in plant right-hand sides on the extended state [x; w; u] */
+enum { CLR_PLANT_UNICYCLE = 1, CLR_PLANT_TORA = 2, CLR_PLANT_ACC = 3, CLR_PLANT_INVPEND = 4 };
+/* ODE algorithms */
+enum { CLR_ALG_TSIT5 = 0, CLR_ALG_RK4 = 1 };
+/* flags */
+enum {
+    CLR_FLAG_DEVICE_IO = 1,   /* every data pointer (inputs and outputs) is a DEVICE pointer; the call
+                                 only enqueues work on clr_stream(ctx) and does not synchronise */
+    CLR_FLAG_NO_STATS = 2     /* skip the per-layer statistics (stats may then be NULL) */
+};
+
+typedef struct clr_ctx clr_ctx;
+typedef struct clr_net clr_net;
+
+/* Pre/post-processing of controller_forward (src/solve.jl:211, :213).  Always HOST pointers. */
+typedef struct {
+    int32_t pre_rows;        /* 0 = identity; else x -> preA*x + preb with preA pre_rows x n (col-major) */
+    const double* preA;
+    const double* preb;
+    int32_t post_kind;       /* CLR_POST_* */
+    int32_t post_rows;       /* rows of postA (MATRIX) or length of post_dims (PROJECT) */
+    const double* postA;     /* SCALE: postA[0]; MATRIX: post_rows x m col-major */
+    const double* postb;     /* SHIFT: postb[0] */
+    const int32_t* post_dims;/* PROJECT: 0-based output rows kept */
+} clr_prepost;
+
+/* Per-call statistics (same layout as the CPU oracle's). */
+typedef struct {
+    int64_t n_cells;
+    int64_t sum_p_in[CLR_MAX_LAYERS];     /* generator columns entering network layer l, summed over cells
+                                             (zero columns excluded, as after remove_zero_columns) */
+    int64_t sum_unstable[CLR_MAX_LAYERS]; /* generators appended by the activation of layer l */
+    int64_t near_threshold;               /* ReLU neurons with |l| or |u| < 1e-12 (branch could flip) */
+    int64_t max_p_out;                    /* largest generator count of an output zonotope */
+    double flops;                         /* sum_l 2 m_l n_l (p_l + 1) over all cells */
+} clr_stats;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int32_t clr_create(int32_t device, clr_ctx** out);
+void clr_destroy(clr_ctx* ctx);
+/* message of the last error on this ctx (or of the last failed clr_create when ctx == NULL) */
+const char* clr_last_error(const clr_ctx* ctx);
+/* the cudaStream_t all work of this ctx is enqueued on */
+void* clr_stream(clr_ctx* ctx);
+int32_t clr_synchronize(clr_ctx* ctx);
+/* number of kernel launches issued by this ctx so far */
+int64_t clr_launch_count(const clr_ctx* ctx);
+/* device memory owned by the library: for callers that keep inputs/outputs resident (CLR_FLAG_DEVICE_IO) */
+int32_t clr_device_alloc(clr_ctx* ctx, int64_t bytes, void** out);
+int32_t clr_device_free(clr_ctx* ctx, void* p);
+int32_t clr_memcpy_h2d(clr_ctx* ctx, void* dst, const void* src, int64_t bytes);
+int32_t clr_memcpy_d2h(clr_ctx* ctx, void* dst, const void* src, int64_t bytes);
+/* tuning knob of the DeepZ tile scheduler: cells per tile (0 = automatic) */
+int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells);
+
+/* ---- networks ------------------------------------------------------------------------------ */
+/* dims has n_layers+1 entries; W[l] is dims[l+1] x dims[l] column-major, b[l] has dims[l+1] entries */
+int32_t clr_net_upload(clr_ctx* ctx, int32_t n_layers, const int32_t* dims, const int32_t* act,
+                       const double* const* W, const double* const* b, clr_net** out);
+void clr_net_free(clr_net* net);
+
+/* ---- DeepZ over the cells of a box split --------------------------------------------------- */
+/*
+ * Cells are the elements of split(H, partition) in Iterators.product order (dimension 1 fastest).
+ * centers / radii are the concatenated per-dimension tables (sum(partition) entries each): cell with
+ * block index k_d in dimension d has centre centers[base_d + k_d] and radius radii[base_d + k_d]
+ * (uniform splits repeat one radius per dimension; cut-point splits do not).  A zero radius drops
+ * that dimension's generator (convert(Zonotope, H)).  Only cells [cell_begin, cell_begin+cell_count)
+ * are processed: this is the shard of one GPU.
+ *
+ * out_lo / out_hi: m_out x cell_count, the box of U = controller_forward(cell)  (src/solve.jl:214-216,
+ * src/setops.jl:76-83).  hull_lo / hull_hi (m_out, may be NULL): min / max over the processed cells.
+ * keep_cap > 0 additionally keeps every output zonotope (at most keep_cap generators) on the device
+ * for clr_deepz_fetch_zonotopes.
+ */
+int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net, int32_t n, const int32_t* partition,
+                          const double* centers, const double* radii, int64_t cell_begin,
+                          int64_t cell_count, const clr_prepost* pp, double* out_lo, double* out_hi,
+                          double* hull_lo, double* hull_hi, clr_stats* stats, int32_t keep_cap,
+                          int32_t flags);
+
+/* ---- DeepZ over explicit zonotopes ----------------------------------------------------------- */
+/* C: n x N centres; generators of cell i are columns col_off[i] .. col_off[i+1]-1 of G (n x col_off[N]) */
+int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net, int32_t n, int64_t N, const double* C,
+                            const int64_t* col_off, const double* G, const clr_prepost* pp,
+                            double* out_lo, double* out_hi, double* hull_lo, double* hull_hi,
+                            clr_stats* stats, int32_t keep_cap, int32_t flags);
+
+/*
+ * Output zonotopes of the last keep_cap > 0 run: out_ncols (N), out_c (m_out x N),
+ * out_G (m_out x keep_cap x N: generator j of cell i at out_G + (i*keep_cap + j)*m_out).
+ * Zero generators are removed (remove_zero_columns) and the reference's column order is kept:
+ * propagated input generators first, then the generators appended by each activation layer in
+ * ascending neuron order.  HOST pointers.
+ */
+int32_t clr_deepz_fetch_zonotopes(clr_ctx* ctx, int32_t* out_ncols, double* out_c, double* out_G);
+
+/* ---- pointwise controller -------------------------------------------------------------------- */
+/* X: nx x N, U: m_out x N */
+int32_t clr_forward_points(clr_ctx* ctx, const clr_net* net, const clr_prepost* pp, int32_t nx,
+                           int64_t N, const double* X, double* U, int32_t flags);
+
+/* ---- simulate(): batched closed-loop rollouts ------------------------------------------------- */
+/*
+ * x0: n_state x N.  Wd: n_dist x N x iters (fresh disturbance per period, src/simulate.jl:110-115) or NULL.
+ * Period it integrates [t0 + it*tau, t0 + (it+1)*tau], the last one ends at T (src/simulate.jl:126).
+ * alg = CLR_ALG_TSIT5: adaptive Tsit5 with OrdinaryDiffEq's default PI controller (abstol, reltol;
+ * pow_mode 1 = DiffEqBase fastpow, 0 = exact pow); alg = CLR_ALG_RK4: `substeps` fixed steps per period.
+ * X_end: n_state x N x iters, U: n_ctrl x N x iters; naccept / nreject (N x iters, may be NULL).
+ * log_cap > 0 records the accepted steps of every period (piece.t / piece.u of the reference's
+ * ODESolution pieces): log_n (N x iters), log_t (log_cap x N x iters), log_u (n_ext x log_cap x N x iters).
+ */
+int32_t clr_rollout(clr_ctx* ctx, const clr_net* net, const clr_prepost* pp, int32_t plant,
+                    int32_t n_state, int32_t n_dist, int32_t n_ctrl, int64_t N, int32_t iters,
+                    const double* x0, const double* Wd, double t0, double tau, double T, int32_t alg,
+                    double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end,
+                    double* U, int32_t* naccept, int32_t* nreject, int32_t log_cap, int32_t* log_n,
+                    double* log_t, double* log_u, int32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLR_B200_H */

@@ -1,0 +1,253 @@
+"""GPU parity tests of the DeepZ path: libclr_b200 (through the C ABI) against the CPU oracle and
+the committed golden fixtures.  Tolerances (BASELINE.json north_star): output boxes 1e-10 absolute,
+centres / generators 1e-12 relative to the zonotope's scale, cell ordering bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_net
+import vcas_kat
+
+pytestmark = pytest.mark.gpu
+
+BOX_ATOL = 1e-10
+TORA_LO, TORA_HI = [0.6, -0.7, -0.4, 0.5], [0.7, -0.6, -0.3, 0.6]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from clr_b200 import runtime
+    c = runtime.Context(0)
+    yield c
+    c.close()
+
+
+def _oracle():
+    from oracle import cbind
+    return cbind
+
+
+def _cmp_boxes(got, ref, atol=BOX_ATOL):
+    np.testing.assert_allclose(got["lo"], ref["lo"], rtol=0, atol=atol)
+    np.testing.assert_allclose(got["hi"], ref["hi"], rtol=0, atol=atol)
+
+
+def test_tora_boxgrid_golden_and_oracle(ctx):
+    import clr_b200
+    z = np.load(os.path.join(GOLDEN, "tora_oracle.npz"))
+    net = load_net("TORA_ReLU")
+    dn = ctx.upload(net)
+    on = _oracle().Net(net.as_tuples())
+    for tag, part in (("p4435", [4, 4, 3, 5]), ("p1010101", [10, 10, 10, 1])):
+        g = clr_b200.split_box(TORA_LO, TORA_HI, part)
+        got = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, post=("shift", -10.0), hull=True)
+        np.testing.assert_allclose(got["lo"], z[f"{tag}_lo"], rtol=0, atol=BOX_ATOL)
+        np.testing.assert_allclose(got["hi"], z[f"{tag}_hi"], rtol=0, atol=BOX_ATOL)
+        ref = _oracle().deepz_boxgrid(on, g.partition, g.centers, g.radii, post=("shift", -10.0))
+        _cmp_boxes(got, ref)
+        assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"]
+        assert got["stats"]["sum_unstable"] == ref["stats"]["sum_unstable"]
+        assert got["stats"]["flops"] == ref["stats"]["flops"]
+        assert got["hull_lo"][0] == got["lo"].min() and got["hull_hi"][0] == got["hi"].max()
+
+
+def test_quadrotor_sigmoid_zonotope_fetch(ctx):
+    import clr_b200
+    z = np.load(os.path.join(GOLDEN, "quadrotor_oracle.npz"))
+    net = load_net("Quadrotor")
+    dn = ctx.upload(net)
+    r = 0.01 * np.array([0.4] * 6 + [0.0] * 6)
+    g = clr_b200.split_box(-r, r, [2] * 6 + [1] * 6)
+    got = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, keep_cap=256)
+    np.testing.assert_allclose(got["lo"], z["lo"], rtol=0, atol=BOX_ATOL)
+    np.testing.assert_allclose(got["hi"], z["hi"], rtol=0, atol=BOX_ATOL)
+    p = got["ncols"][0]
+    assert p == z["cell0_G"].shape[1] == 6 + 64 * 3
+    scale = np.abs(z["cell0_G"]).max()
+    np.testing.assert_allclose(got["G"][0, :p, :].T, z["cell0_G"], rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(got["c"][0], z["cell0_c"], rtol=1e-12, atol=1e-14)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii, keep_cap=256)
+    assert np.array_equal(got["ncols"], ref["ncols"])
+    np.testing.assert_allclose(got["G"], ref["G"], rtol=0, atol=1e-12 * scale)
+
+
+def test_vcas_verdicts(ctx):
+    nets = [ctx.upload(load_net(f"VerticalCAS_{i}")) for i in range(1, 10)]
+
+    def fh(adv, c, G):
+        r = ctx.deepz_zonotopes(nets[adv], c[None, :], [0, G.shape[1]], G.T)
+        return r["hi"][0]
+
+    for hdot0, want in vcas_kat.EXPECTED.items():
+        verdict, _ = vcas_kat.run_instance(hdot0, fh)
+        assert verdict == want, (hdot0, verdict)
+
+
+@pytest.mark.parametrize("name,post", [("TORA_ReLU", ("shift", -10.0)), ("TORA_sigmoid", ("scale", 11.0)),
+                                       ("TORA_ReLUtanh", ("scale", 11.0)), ("Unicycle", ("shift", -20.0)),
+                                       ("AttitudeControl", None), ("InvertedPendulum", None)])
+def test_random_zonotopes_vs_oracle(ctx, name, post):
+    from clr_b200 import workloads
+    net = load_net(name)
+    n = net.dim_in
+    rng = np.random.default_rng(11)
+    C, off, G = workloads.random_zonotopes(rng, 300, n, 0, 14, -0.6, 0.6, 0.02)
+    got = ctx.deepz_zonotopes(ctx.upload(net), C, off, G, post=post, keep_cap=600)
+    ref = _oracle().deepz_zonotopes(_oracle().Net(net.as_tuples()), C, off, G, post=post, keep_cap=600)
+    _cmp_boxes(got, ref)
+    assert np.array_equal(got["ncols"], ref["ncols"])
+    scale = max(np.abs(ref["G"]).max(), 1e-300)
+    np.testing.assert_allclose(got["G"], ref["G"], rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(got["c"], ref["c"], rtol=0, atol=1e-12 * max(np.abs(ref["c"]).max(), scale))
+    assert got["stats"]["sum_unstable"] == ref["stats"]["sum_unstable"]
+    assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"]
+
+
+def test_acc_affine_preprocessing(ctx):
+    """ACC: x -> [30, 1.4, M x] (models/ACC/ACC.jl:81-99) folded in as an affine pre-layer."""
+    net = load_net("ACC_relu")
+    A = np.zeros((5, 6))
+    A[2, 4] = 1.0                      # v_ego
+    A[3, 0], A[3, 3] = 1.0, -1.0       # D_rel = x_lead - x_ego
+    A[4, 1], A[4, 4] = 1.0, -1.0       # v_rel
+    d = np.array([30.0, 1.4, 0.0, 0.0, 0.0])
+    rng = np.random.default_rng(5)
+    from clr_b200 import workloads
+    C, off, G = workloads.random_zonotopes(rng, 200, 6, 2, 14, 0.0, 1.0, 0.05)
+    C += np.array([90.0, 32.0, 0.0, 10.0, 30.0, 0.0])
+    got = ctx.deepz_zonotopes(ctx.upload(net), C, off, G, pre=(A, d))
+    ref = _oracle().deepz_zonotopes(_oracle().Net(net.as_tuples()), C, off, G, pre=(A, d))
+    _cmp_boxes(got, ref)
+    assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"]
+
+
+@pytest.mark.parametrize("post", [("matrix", np.array([[1.0, -2.0, 0.5], [0.0, 1.0, 1.0]])),
+                                  ("matrix", np.array([[0.3, -0.2, 1.5]])),
+                                  ("project", [2, 0]), ("project", [1])])
+def test_matrix_and_projection_postprocessing(ctx, post):
+    import clr_b200
+    net = load_net("Quadrotor")
+    r = 0.01 * np.array([0.4] * 6 + [0.0] * 6)
+    g = clr_b200.split_box(-r, r, [2, 2, 2] + [1] * 9)
+    got = ctx.deepz_boxgrid(ctx.upload(net), g.partition, g.centers, g.radii, post=post, keep_cap=256)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii, post=post,
+                                  keep_cap=256)
+    _cmp_boxes(got, ref)
+    assert np.array_equal(got["ncols"], ref["ncols"])
+    np.testing.assert_allclose(np.abs(got["G"]), np.abs(ref["G"]), rtol=0, atol=1e-12 * np.abs(ref["G"]).max())
+
+
+@pytest.mark.parametrize("regime,count", [("stable", 3000), ("mixed", 600), ("dense", 160)])
+def test_c4_synthetic_regimes(ctx, regime, count):
+    """6 -> 100^4 -> 1 ReLU net of BASELINE's scaling config: small tiles, overflow retries and
+    (dense regime) the global-store pass for cells that do not fit in shared memory."""
+    from clr_b200 import workloads
+    net = workloads.synthetic_relu_net()
+    g = workloads.c4_grid(regime, last_dim_blocks=1)
+    begin = 12345
+    got = ctx.deepz_boxgrid(ctx.upload(net), g.partition, g.centers, g.radii, cell_begin=begin, cell_count=count,
+                            hull=True)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii,
+                                  cell_begin=begin, cell_count=count)
+    scale = max(1.0, np.abs(ref["hi"]).max())
+    _cmp_boxes(got, ref, atol=BOX_ATOL * scale)
+    assert got["stats"]["sum_unstable"] == ref["stats"]["sum_unstable"]
+    assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"]
+    assert got["hull_lo"][0] == got["lo"].min() and got["hull_hi"][0] == got["hi"].max()
+
+
+def test_cut_point_partition_and_flat_dims(ctx):
+    """Cut-point BoxSplitter (models/InvertedPendulum/InvertedPendulum.jl:210) and zero-radius blocks."""
+    import clr_b200
+    net = load_net("InvertedPendulum")
+    g = clr_b200.split_box([1.0, 0.0], [1.2, 0.2], [[1.1, 1.16], [0.09, 0.145, 0.18]])
+    assert len(g) == 12
+    got = ctx.deepz_boxgrid(ctx.upload(net), g.partition, g.centers, g.radii)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii)
+    _cmp_boxes(got, ref)
+    g2 = clr_b200.split_box([1.0, 0.1], [1.2, 0.1], [4, 1])          # second dimension is flat
+    got = ctx.deepz_boxgrid(ctx.upload(net), g2.partition, g2.centers, g2.radii)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g2.partition, g2.centers, g2.radii)
+    _cmp_boxes(got, ref)
+    assert got["stats"]["sum_p_in"][0] == 4
+
+
+def test_degenerate_cells_equal_pointwise_forward(ctx):
+    rng = np.random.default_rng(1)
+    for name in ("TORA_ReLU", "ACC_tanh", "Quadrotor", "Unicycle"):
+        net = load_net(name)
+        dn = ctx.upload(net)
+        X = rng.uniform(-1, 1, (50, net.dim_in))
+        r = ctx.deepz_zonotopes(dn, X, np.zeros(51, dtype=np.int64), np.zeros((0, net.dim_in)))
+        u = ctx.forward_points(dn, X)
+        np.testing.assert_allclose(r["lo"], u, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(r["hi"], u, rtol=1e-12, atol=1e-14)
+
+
+def test_shards_concatenate_to_the_full_result(ctx):
+    import clr_b200
+    net = load_net("TORA_ReLU")
+    dn = ctx.upload(net)
+    g = clr_b200.split_box(TORA_LO, TORA_HI, [10, 10, 10, 1])
+    full = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, post=("shift", -10.0))
+    parts = []
+    for rank in range(3):
+        b, cnt = g.shard(rank, 3)
+        parts.append(ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=b, cell_count=cnt,
+                                       post=("shift", -10.0))["lo"])
+    assert np.array_equal(np.concatenate(parts), full["lo"])      # bit-exact, ordering included
+    ctx.set_tile_cells(1)
+    one = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, post=("shift", -10.0))
+    ctx.set_tile_cells(0)
+    assert np.array_equal(one["lo"], full["lo"]) and np.array_equal(one["hi"], full["hi"])
+
+
+def test_empty_and_error_paths(ctx):
+    import clr_b200
+    from clr_b200 import runtime
+    net = load_net("TORA_ReLU")
+    dn = ctx.upload(net)
+    g = clr_b200.split_box(TORA_LO, TORA_HI, [2, 2, 2, 2])
+    out = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=3, cell_count=0)
+    assert out["lo"].shape == (0, 1)
+    with pytest.raises(runtime.ClrArgumentError):
+        ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=10, cell_count=10)
+    g3 = clr_b200.split_box([0, 0, 0], [1, 1, 1], [2, 2, 2])
+    with pytest.raises(runtime.ClrArgumentError):
+        ctx.deepz_boxgrid(dn, g3.partition, g3.centers, g3.radii)       # 3-dim cells into a 4-input net
+    ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii)
+    with pytest.raises(runtime.ClrError):
+        ctx.fetch_zonotopes(16, 1, 4)                                    # nothing was kept by the last run
+    quad = load_net("Quadrotor")
+    r = 0.01 * np.array([0.4] * 6 + [0.0] * 6)
+    gq = clr_b200.split_box(-r, r, [2] + [1] * 11)
+    with pytest.raises(runtime.ClrError):
+        ctx.deepz_boxgrid(ctx.upload(quad), gq.partition, gq.centers, gq.radii, keep_cap=4)   # 198 generators
+
+
+def test_full_size_properties(ctx):
+    """BASELINE size (10^6 cells, 6 -> 100^4 -> 1): soundness by sampling, shard consistency and
+    monotonicity of the hull, none of which needs the oracle at this size."""
+    from clr_b200 import workloads
+    net = workloads.synthetic_relu_net()
+    dn = ctx.upload(net)
+    g = workloads.c4_grid("stable")
+    assert len(g) == 10 ** 6
+    out = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, hull=True)
+    assert np.all(out["lo"] <= out["hi"])
+    assert out["hull_lo"][0] == out["lo"].min() and out["hull_hi"][0] == out["hi"].max()
+    rng = np.random.default_rng(7)
+    ids = rng.integers(0, len(g), 2000)
+    X = np.empty((2000, 6))
+    for k, i in enumerate(ids):
+        c, r = g.cell(int(i))
+        X[k] = c + r * rng.uniform(-1, 1, 6)
+    U = ctx.forward_points(dn, X)
+    assert np.all(U[:, 0] >= out["lo"][ids, 0] - 1e-9) and np.all(U[:, 0] <= out["hi"][ids, 0] + 1e-9)
+    b, cnt = g.shard(5, 8)
+    part = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=b, cell_count=cnt)
+    assert np.array_equal(part["lo"], out["lo"][b:b + cnt]) and np.array_equal(part["hi"], out["hi"][b:b + cnt])
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii,
+                                  cell_begin=b, cell_count=2000)
+    np.testing.assert_allclose(part["lo"][:2000], ref["lo"], rtol=0, atol=BOX_ATOL)

@@ -1,0 +1,90 @@
+"""GPU parity tests of the simulate() path (clr_rollout / clr_forward_points) against the CPU oracle.
+Tolerance (north_star): trajectories within 1e-10 for identical inputs; step counts identical."""
+import numpy as np
+import pytest
+
+from conftest import load_net
+
+pytestmark = pytest.mark.gpu
+TRAJ_ATOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from clr_b200 import runtime
+    c = runtime.Context(0)
+    yield c
+    c.close()
+
+
+def _oracle():
+    from oracle import cbind
+    return cbind
+
+
+@pytest.mark.parametrize("name,pre,post", [("Unicycle", None, ("shift", -20.0)), ("TORA_ReLU", None, ("shift", -10.0)),
+                                            ("TORA_sigmoid", None, ("scale", 11.0)), ("Quadrotor", None, None),
+                                            ("AttitudeControl", None, ("project", [2, 0]))])
+def test_forward_points(ctx, name, pre, post):
+    net = load_net(name)
+    X = np.random.default_rng(3).uniform(-1, 1, (1000, net.dim_in))
+    got = ctx.forward_points(ctx.upload(net), X, pre=pre, post=post)
+    ref = _oracle().forward_points(_oracle().Net(net.as_tuples()), X, pre=pre, post=post)
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("alg", ["Tsit5", "RK4"])
+def test_unicycle_rollout(ctx, alg):
+    from clr_b200 import workloads
+    net = load_net("Unicycle")
+    rng = np.random.default_rng(5)
+    N, iters = 2000, 50
+    x0, Wd = workloads.unicycle_samples(rng, N, iters)
+    got = ctx.rollout(ctx.upload(net), "Unicycle", x0, Wd, 0.0, 0.2, 10.0, iters, alg=alg, post=("shift", -20.0))
+    ref = _oracle().rollout(_oracle().Net(net.as_tuples()), "Unicycle", 4, 1, 2, x0, Wd, 0.0, 0.2, 10.0, iters, alg=alg,
+                            post=("shift", -20.0))
+    assert np.array_equal(got["naccept"], ref["naccept"]) and np.array_equal(got["nreject"], ref["nreject"])
+    np.testing.assert_allclose(got["X_end"], ref["X_end"], rtol=0, atol=TRAJ_ATOL)
+    np.testing.assert_allclose(got["U"], ref["U"], rtol=0, atol=TRAJ_ATOL)
+
+
+def test_step_log_matches_oracle(ctx):
+    from clr_b200 import workloads
+    net = load_net("Unicycle")
+    x0, Wd = workloads.unicycle_samples(np.random.default_rng(6), 64, 4)
+    got = ctx.rollout(ctx.upload(net), "Unicycle", x0, Wd, 0.0, 0.2, 0.75, 4, post=("shift", -20.0), log_cap=16)
+    ref = _oracle().rollout(_oracle().Net(net.as_tuples()), "Unicycle", 4, 1, 2, x0, Wd, 0.0, 0.2, 0.75, 4,
+                            post=("shift", -20.0), log_cap=16)
+    assert np.array_equal(got["log_n"], ref["log_n"])
+    for it in range(4):
+        for j in range(64):
+            k = ref["log_n"][it, j]
+            np.testing.assert_allclose(got["log_t"][it, j, :k], ref["log_t"][it, j, :k], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(got["log_u"][it, j, :k], ref["log_u"][it, j, :k], rtol=0, atol=TRAJ_ATOL)
+    # the last period is shorter: it ends at T = 0.75 (src/simulate.jl:126)
+    assert abs(got["log_t"][3, 0, got["log_n"][3, 0] - 1] - 0.75) < 1e-15
+
+
+@pytest.mark.parametrize("plant,name,post,lo,hi", [
+    ("TORA", "TORA_ReLU", ("shift", -10.0), [0.6, -0.7, -0.4, 0.5], [0.7, -0.6, -0.3, 0.6]),
+    ("InvertedPendulum", "InvertedPendulum", None, [1.0, 0.0], [1.2, 0.2])])
+def test_other_plants(ctx, plant, name, post, lo, hi):
+    net = load_net(name)
+    rng = np.random.default_rng(8)
+    x0 = rng.uniform(lo, hi, (500, len(lo)))
+    tau = 1.0 if plant == "TORA" else 0.05
+    got = ctx.rollout(ctx.upload(net), plant, x0, None, 0.0, tau, 10 * tau, 10, post=post)
+    ref = _oracle().rollout(_oracle().Net(net.as_tuples()), plant, len(lo), 0, 1, x0, None, 0.0, tau, 10 * tau, 10, post=post)
+    assert np.array_equal(got["naccept"], ref["naccept"])
+    np.testing.assert_allclose(got["X_end"], ref["X_end"], rtol=0, atol=TRAJ_ATOL)
+
+
+def test_rollout_argument_errors(ctx):
+    from clr_b200 import runtime
+    net = load_net("Unicycle")
+    dn = ctx.upload(net)
+    x0 = np.zeros((4, 4))
+    with pytest.raises(runtime.ClrArgumentError):
+        ctx.rollout(dn, "TORA", x0, None, 0.0, 0.2, 1.0, 5)                # 2 controller outputs, TORA takes 1
+    with pytest.raises(runtime.ClrError):
+        ctx.rollout(dn, "Unicycle", x0, np.zeros((5, 4, 1)), 0.0, 0.2, 1.0, 5, post=("shift", -20.0), log_cap=1)
