@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of ClosedLoopReachability.jl on B200: zonotope controller propagations/s.
+
+A "step" is one pass of the hot path over one batch of synthetic input: every split cell of the
+C4 scaling configuration (BASELINE.json configs[3]: 10^6 box cells through a 6-input 4x100 ReLU
+network, Float64) goes through controller_forward with DeepZ on the GPU.  Cells are sharded over the
+ranks by contiguous cell-id range (weak scaling: 10^6 cells per GPU); there is no collective on the
+data path, only the final gather of the per-GPU hulls.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm (C restatement of the reference)
+
+One JSON line is printed by rank 0.  `value` = cells x steps / device time with inputs resident in HBM
+(CUDA events on the library's stream, L2 flushed between steps, max over ranks); `e2e` = the same
+metric through the host-buffer API call (H2D of the tables, D2H of all boxes inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DMMA_PEAK_TFLOPS = 37.0   # measured on this pool's B200: profiles/microbench/r01_dmma_bench_b200.txt (mma.sync f64)
+METRIC = "zonotope controller propagations/sec (cells x steps)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--regime", default=os.environ.get("CLR_BENCH_REGIME", "stable"), choices=["stable", "mixed", "dense"])
+    ap.add_argument("--cells-per-dim", type=int, default=10)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the simulate() rollout line")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traj", type=int, default=1000000)
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args, world):
+    """C4: box [c0-s, c0+s]^6 split [10]^6; with N ranks the box is N times longer in the last (slowest)
+    dimension and split 10 N times there, so every rank owns 10^6 cells of identical size."""
+    from clr_b200 import workloads
+    from clr_b200.splitters import split_box
+    net = workloads.synthetic_relu_net()
+    c0, s = {"dense": (0.0, 1.0), "mixed": (0.3, 0.1), "stable": (0.3, 0.01)}[args.regime]
+    k = args.cells_per_dim
+    lo = [c0 - s] * 6
+    hi = [c0 + s] * 5 + [c0 - s + 2 * s * world]
+    grid = split_box(lo, hi, [k] * 5 + [k * world])
+    return net, grid
+
+
+def cpu_baseline(net, grid, budget_s=12.0):
+    """The C restatement of the reference (oracle/, OpenMP over cells, all host cores) on a bounded sample."""
+    from oracle import cbind
+    on = cbind.Net(net.as_tuples())
+    cores = cbind.num_threads()
+    n, chunk, done, t0 = len(grid), 4000, 0, time.perf_counter()
+    cbind.deepz_boxgrid(on, grid.partition, grid.centers, grid.radii, cell_begin=0, cell_count=256)   # warm-up
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and done < n:
+        cnt = min(chunk, n - done)
+        cbind.deepz_boxgrid(on, grid.partition, grid.centers, grid.radii, cell_begin=done, cell_count=cnt)
+        done += cnt
+        chunk = min(chunk * 2, 64000)
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "propagations/s", "cores": cores, "kind": "port",
+            "sample": f"first {done} cells of the same split, {dt:.1f} s, C oracle (OpenMP, -O3)"}
+
+
+def run_reference(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    net, grid = workload(args, 1)
+    from oracle import cbind
+    on = cbind.Net(net.as_tuples())
+    cores = cbind.num_threads()
+    per_step = {"stable": 100000, "mixed": 30000, "dense": 6000}[args.regime]
+    for _ in range(max(args.warmup, 1)):
+        cbind.deepz_boxgrid(on, grid.partition, grid.centers, grid.radii, cell_begin=0, cell_count=per_step // 10)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        b = (s * per_step) % (len(grid) - per_step)
+        cbind.deepz_boxgrid(on, grid.partition, grid.centers, grid.radii, cell_begin=b, cell_count=per_step)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "propagations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4 synthetic scaling, 6->100x4->1 ReLU, regime={args.regime}; bounded sample of "
+                                   f"{per_step} cells per step of the 10^6-cell split"},
+            "cpu_baseline": {"value": v, "unit": "propagations/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} cells per step x {args.steps} steps; the reference is Julia "
+                                       "(absent from this image), so its C restatement in oracle/ is timed"},
+            "e2e": {"value": v, "unit": "propagations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import clr_b200
+    from clr_b200 import _lib, parallel, runtime, workloads
+    rank, local, world = dist_env()
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = runtime.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    net, grid = workload(args, world)
+    dn = ctx.upload(net)
+    b, cnt = parallel.shard_range(len(grid), rank, world)
+    m = 1
+    pp = runtime.PrePostArg(None, None)
+
+    # inputs resident in HBM: the split tables; outputs: boxes + hull, device resident
+    cc = torch.from_numpy(np.concatenate(grid.centers)).to(dev)
+    rr = torch.from_numpy(np.concatenate(grid.radii)).to(dev)
+    d_lo = torch.empty((cnt, m), dtype=torch.float64, device=dev)
+    d_hi = torch.empty((cnt, m), dtype=torch.float64, device=dev)
+    d_hl = torch.empty(m, dtype=torch.float64, device=dev)
+    d_hh = torch.empty(m, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_dev():
+        ctx.deepz_boxgrid_dev(dn, 6, grid.partition, cc, rr, b, cnt, pp, d_lo, d_hi, d_hl, d_hh)
+
+    # algorithmic FLOPs of one step (statistics run, untimed)
+    st = _lib.Stats()
+    ctx.deepz_boxgrid_dev(dn, 6, grid.partition, cc, rr, b, cnt, pp, d_lo, d_hi, d_hl, d_hh, stats=st)
+    ctx.synchronize()
+    flops_step = st.flops
+    p_in = [st.sum_p_in[l] / cnt for l in range(5)]
+
+    ctx.set_profiling(True)
+    for _ in range(args.warmup):
+        step_dev()
+    ctx.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    pass_ms = np.zeros(3)
+    retried = big = 0
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()                       # L2 flush between timed iterations (not timed)
+            ev0[s].record(stream)
+            step_dev()
+            ev1[s].record(stream)
+        info = ctx.last_pass_info()
+        pass_ms += np.array(info["pass_ms"])
+        retried, big = info["retried"], info["big"]
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(bb) for a, bb in zip(ev0, ev1))
+    if world > 1:
+        dist.barrier()
+    t_ms = parallel.max_over_ranks(dev_ms, device=dev)
+    total_cells = parallel.sum_over_ranks(cnt, device=dev)
+    value = total_cells * args.steps / (t_ms * 1e-3)
+    # final gather of the per-GPU hulls over NCCL (the only communication of the path)
+    hl, hh = parallel.gather_hull(d_hl, d_hh)
+    hull = [float(hl[0]), float(hh[0])]
+
+    # ---- end to end: host buffers through the public API (blocking call) -------------------------------
+    out_lo = torch.empty((cnt, m), dtype=torch.float64).pin_memory().numpy()
+    out_hi = torch.empty((cnt, m), dtype=torch.float64).pin_memory().numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    ctx.deepz_boxgrid(dn, grid.partition, grid.centers, grid.radii, cell_begin=b, cell_count=cnt, stats=False,
+                      out_lo=out_lo, out_hi=out_hi)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.deepz_boxgrid(dn, grid.partition, grid.centers, grid.radii, cell_begin=b, cell_count=cnt, stats=False,
+                          out_lo=out_lo, out_hi=out_hi)
+    torch.cuda.synchronize()
+    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, device=dev)
+    tab_bytes = 2 * 8 * int(np.sum(grid.partition))
+    e2e = {"value": total_cells * e2e_steps / e2e_s, "unit": "propagations/s", "steps": e2e_steps,
+           "h2d_bytes_per_step": tab_bytes, "d2h_bytes_per_step": int(2 * 8 * m * cnt),
+           "note": "clr_deepz_boxgrid with host buffers: H2D of the split tables, D2H of every cell's box, blocking"}
+    assert np.array_equal(out_lo, d_lo.cpu().numpy())
+
+    # ---- roofline of the dominant kernel (main-pass deepz_kernel, or the big-cell pass in the dense regime) ----
+    dom = int(np.argmax(pass_ms))
+    dom_ms = pass_ms[dom] / args.steps
+    ach = flops_step / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": ["deepz_kernel (main pass, smem store)", "deepz_kernel (retry pass)",
+                                              "deepz_kernel (big-cell pass, global store)"][dom],
+                "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / DMMA_PEAK_TFLOPS,
+                "traffic": None,
+                "peak_source": "FP64 mma.sync (DMMA) issue peak measured on this pool's B200 "
+                               "(profiles/microbench/r01_dmma_bench_b200.txt; cuBLAS DGEMM 8192^3 = 35.5); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "algorithmic_flops_per_step": flops_step, "kernel_ms_per_step": dom_ms,
+                "pass_ms_per_step": (pass_ms / args.steps).tolist(), "mean_generators_in": p_in,
+                "cells_retried": int(retried), "cells_big": int(big)}
+
+    line = {"metric": METRIC, "value": value, "unit": "propagations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4 synthetic scaling: {cnt} box cells per GPU (split [10]^5 x [10 N] of a 6-dim box), "
+                                   f"6->100x4->1 ReLU network (seed 4), Float64 DeepZ, regime={args.regime}",
+                       "cells_per_gpu": cnt, "regime": args.regime, "l2": "256 MB buffer written between timed steps",
+                       "hull": hull},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "wall_s_timed_region": wall}
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(net, grid)
+    elif rank == 0:
+        line["cpu_baseline"] = None
+
+    # ---- secondary metric: simulate() rollouts (Unicycle, 10^6 trajectories x 50 periods) -----------------
+    if not args.no_secondary:
+        uni = clr_b200.FeedforwardNetwork.load_npz(os.path.join(ROOT, "tests", "golden", "nets", "Unicycle.npz"))
+        du = ctx.upload(uni)
+        N, iters = args.traj, 50
+        rng = np.random.default_rng(5 + rank)
+        x0, Wd = workloads.unicycle_samples(rng, N, iters)
+        d_x0 = torch.from_numpy(x0).to(dev)
+        d_Wd = torch.from_numpy(Wd).to(dev)
+        d_X = torch.empty((iters, N, 4), dtype=torch.float64, device=dev)
+        d_U = torch.empty((iters, N, 2), dtype=torch.float64, device=dev)
+        ppu = runtime.PrePostArg(None, ("shift", -20.0))
+        res = {}
+        for alg in ("Tsit5", "RK4"):
+            def roll():
+                ctx.rollout_dev(du, "Unicycle", N, iters, d_x0, d_Wd, 0.0, 0.2, 10.0, alg, 1e-6, 1e-3, 4, 1, ppu, d_X, d_U)
+            roll()
+            ctx.synchronize()
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            with torch.cuda.stream(stream):
+                a.record(stream)
+                for _ in range(reps):
+                    roll()
+                c.record(stream)
+            ctx.synchronize()
+            ms = parallel.max_over_ranks(a.elapsed_time(c) / reps, device=dev)
+            byts = 88.0 * N * iters
+            res[alg] = {"value": world * N / (ms * 1e-3), "unit": "trajectories/s", "ms": ms,
+                        "hbm_GBps_algorithmic": byts / (ms * 1e-3) / 1e9}
+        line["secondary"] = {"metric": "sim trajectories/sec", "config": f"Unicycle, {N} trajectories per GPU x {iters} "
+                             "control periods, 4->500->2 ReLU controller; Tsit5 = the reference's solver, RK4 = 4 fixed steps / period",
+                             **res}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

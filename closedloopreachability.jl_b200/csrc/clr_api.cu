@@ -76,6 +76,11 @@ struct clr_ctx {
     int64_t keep_cells = 0;
     int keep_cap = 0, keep_m = 0;
     int* d_err = nullptr;
+    // optional per-pass timing of the last DeepZ call (clr_set_profiling)
+    int profiling = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float pass_ms[3] = {0.f, 0.f, 0.f};
+    int64_t last_retry = 0, last_big = 0;
 };
 
 namespace {
@@ -421,12 +426,22 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     int grid = (int)std::min<long long>(ctx->sms, N);
     int rc;
     sp.pass = 0;
+    ctx->pass_ms[0] = ctx->pass_ms[1] = ctx->pass_ms[2] = 0.f;
+    if (ctx->profiling) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 16, c->dev, in, out, sp))) return rc;
+    if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
     if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 16, c->dev, in, out, sp))) return rc;
+    if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     // how many cells did not fit in shared memory at all?
     CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->profiling) {
+        CU(cudaEventElapsedTime(&ctx->pass_ms[0], ctx->ev[0], ctx->ev[1]));
+        CU(cudaEventElapsedTime(&ctx->pass_ms[1], ctx->ev[1], ctx->ev[2]));
+    }
+    ctx->last_retry = (int64_t)ctx->h_state->n_retry;
+    ctx->last_big = (int64_t)ctx->h_state->n_big;
     if (ctx->h_state->n_big > 0) {
         const int wc = worst_cols(D, p0max);
         DeepzSched sg = sp;
@@ -436,9 +451,12 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         size_t need = sizeof(double) * (size_t)gridg * 2 * sg.cap;
         if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, need))) return rc;
         sg.workspace = ctx->d_ws;
+        if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         if ((rc = launch_deepz(ctx, true, want_stats, c->ksreg, gridg, threads, dz_meta_bytes(want_stats), c->dev, in, out, sg))) return rc;
+        if (ctx->profiling) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->profiling) CU(cudaEventElapsedTime(&ctx->pass_ms[2], ctx->ev[2], ctx->ev[3]));
     }
     if (ctx->h_state->error == CLR_ERR_CAPACITY && keep_cap > 0)
         return fail(ctx, CLR_ERR_CAPACITY, "an output zonotope has more than keep_cap = %d generators (max_p_out = %d)", keep_cap,
@@ -515,6 +533,7 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_err, sizeof(int));
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e != cudaSuccess) {
         int rc = fail(nullptr, CLR_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
         delete c;
@@ -539,6 +558,7 @@ void clr_destroy(clr_ctx* ctx) {
     cudaFree(ctx->d_keepC);
     cudaFree(ctx->d_keepG);
     cudaFree(ctx->d_err);
+    for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -584,6 +604,19 @@ int32_t clr_memcpy_d2h(clr_ctx* ctx, void* dst, const void* src, int64_t bytes) 
 int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells) {
     if (!ctx || cells < 0 || cells > CLR_TILE_CELLS_MAX) return fail(ctx, CLR_ERR_ARG, "tile cells must be in 0..%d", CLR_TILE_CELLS_MAX);
     ctx->tile_cells = cells;
+    return 0;
+}
+
+int32_t clr_set_profiling(clr_ctx* ctx, int32_t on) {
+    if (!ctx) return CLR_ERR_ARG;
+    ctx->profiling = on != 0;
+    return 0;
+}
+int32_t clr_last_pass_info(clr_ctx* ctx, double* pass_ms, int64_t* retried, int64_t* big) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (pass_ms) for (int i = 0; i < 3; i++) pass_ms[i] = ctx->pass_ms[i];
+    if (retried) *retried = ctx->last_retry;
+    if (big) *big = ctx->last_big;
     return 0;
 }
 

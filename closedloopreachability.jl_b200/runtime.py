@@ -165,12 +165,21 @@ class Context:
     def set_tile_cells(self, cells: int):
         self._check(self.L.clr_set_tile_cells(self.h, int(cells)))
 
+    def set_profiling(self, on: bool):
+        self._check(self.L.clr_set_profiling(self.h, 1 if on else 0))
+
+    def last_pass_info(self):
+        ms = (C.c_double * 3)()
+        retried, big = C.c_int64(), C.c_int64()
+        self._check(self.L.clr_last_pass_info(self.h, ms, C.byref(retried), C.byref(big)))
+        return {"pass_ms": list(ms), "retried": retried.value, "big": big.value}
+
     def upload(self, net: FeedforwardNetwork) -> DeviceNetwork:
         return DeviceNetwork(self, net)
 
     # ---- DeepZ ------------------------------------------------------------------------------------
     def deepz_boxgrid(self, dnet: DeviceNetwork, partition, centers, radii, cell_begin=0, cell_count=None,
-                      pre=None, post=None, hull=False, stats=True, keep_cap=0, boxes=True):
+                      pre=None, post=None, hull=False, stats=True, keep_cap=0, boxes=True, out_lo=None, out_hi=None):
         """All cells [cell_begin, cell_begin+cell_count) of a box split through controller_forward.
 
         ``centers`` / ``radii``: per-dimension tables (lists of 1-D arrays; ``radii`` per block).
@@ -188,8 +197,8 @@ class Context:
         pp = PrePostArg(pre, post)
         m = pp.out_dim(dnet.dims[-1])
         cnt = max(int(cell_count), 0)
-        lo = np.empty((cnt, m)) if boxes else None
-        hi = np.empty((cnt, m)) if boxes else None
+        lo = (out_lo if out_lo is not None else np.empty((cnt, m))) if boxes else None
+        hi = (out_hi if out_hi is not None else np.empty((cnt, m))) if boxes else None
         hl = np.empty(m) if hull else None
         hh = np.empty(m) if hull else None
         st = _lib.Stats() if stats else None

@@ -107,6 +107,11 @@ int32_t clr_memcpy_h2d(clr_ctx* ctx, void* dst, const void* src, int64_t bytes);
 int32_t clr_memcpy_d2h(clr_ctx* ctx, void* dst, const void* src, int64_t bytes);
 /* tuning knob of the DeepZ tile scheduler: cells per tile (0 = automatic) */
 int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells);
+/* on: CUDA events bracket each pass of the following DeepZ calls (main, retry, big-cell) */
+int32_t clr_set_profiling(clr_ctx* ctx, int32_t on);
+/* device time (ms) of the three passes of the last DeepZ call (needs profiling on), the number of
+   cells that were retried alone and the number that went through the global-store pass */
+int32_t clr_last_pass_info(clr_ctx* ctx, double* pass_ms /*3*/, int64_t* retried, int64_t* big);
 
 /* ---- networks ------------------------------------------------------------------------------ */
 /* dims has n_layers+1 entries; W[l] is dims[l+1] x dims[l] column-major, b[l] has dims[l+1] entries */
