@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "deepz.cuh"
+#include "deepz_launch.h"
 #include "rollout.cuh"
 
 namespace {
@@ -316,34 +316,22 @@ int worst_cols(const DevNet& D, int p0) {
     return worst;
 }
 
-template <int KSREG, bool GLOBAL, bool STATS>
-int launch_deepz_t(clr_ctx* ctx, int grid, int threads, size_t smem, const DevNet* net, const DeepzInput& in,
-                   const DeepzOutput& out, const DeepzSched& sp) {
-    auto kern = deepz_kernel<KSREG, GLOBAL, STATS>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, ctx->stream>>>(net, in, out, ctx->d_state, sp);
-    CU(cudaGetLastError());
-    ctx->launches++;
-    return 0;
-}
+}  // namespace
 
-template <bool GLOBAL, bool STATS>
-int launch_deepz_k(clr_ctx* ctx, int ksreg, int grid, int threads, size_t smem, const DevNet* net,
-                   const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
-    switch (ksreg) {
-        case 8: return launch_deepz_t<8, GLOBAL, STATS>(ctx, grid, threads, smem, net, in, out, sp);
-        case 16: return launch_deepz_t<16, GLOBAL, STATS>(ctx, grid, threads, smem, net, in, out, sp);
-        case 25: return launch_deepz_t<25, GLOBAL, STATS>(ctx, grid, threads, smem, net, in, out, sp);
-        default: return launch_deepz_t<32, GLOBAL, STATS>(ctx, grid, threads, smem, net, in, out, sp);
-    }
-}
+namespace {
 
 int launch_deepz(clr_ctx* ctx, bool global, bool stats, int ksreg, int grid, int threads, size_t smem,
                  const DevNet* net, const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
-    if (global) return stats ? launch_deepz_k<true, true>(ctx, ksreg, grid, threads, smem, net, in, out, sp)
-                             : launch_deepz_k<true, false>(ctx, ksreg, grid, threads, smem, net, in, out, sp);
-    return stats ? launch_deepz_k<false, true>(ctx, ksreg, grid, threads, smem, net, in, out, sp)
-                 : launch_deepz_k<false, false>(ctx, ksreg, grid, threads, smem, net, in, out, sp);
+    cudaError_t e;
+    switch (ksreg) {   // one translation unit per KSREG (deepz_ks*.cu), so that the instantiations compile in parallel
+        case 8: e = launch_deepz_ks8(global, stats, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 16: e = launch_deepz_ks16(global, stats, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 25: e = launch_deepz_ks25(global, stats, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        default: e = launch_deepz_ks32(global, stats, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+    }
+    if (e != cudaSuccess) return fail(ctx, CLR_ERR_CUDA, "DeepZ kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+    return 0;
 }
 
 // Shared driver of clr_deepz_boxgrid / clr_deepz_zonotopes once `in` points at device inputs.
@@ -412,14 +400,18 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     }
     CU(cudaMemsetAsync(ctx->d_state, 0, sizeof(DevCallState), ctx->stream));
 
-    const int threads = c->warps * 32;
+    const int threads = DZ_THREADS;
     const size_t meta = dz_meta_bytes(want_stats);
     const size_t smem_total = (size_t)ctx->smem_optin;
     if (smem_total < meta + 2 * 8 * 64) return fail(ctx, CLR_ERR_CUDA, "device has too little shared memory");
     DeepzSched sp{};
     sp.cap = (int)((smem_total - meta) / 16);
     sp.tile_cells = ctx->tile_cells;
-    sp.items_cells = std::max(1, DZ_IMAX * threads / clr_pad4(D.max_rows));
+    {
+        const int rowsP = clr_pad4(D.max_rows);
+        const int H = (rowsP + threads - 1) / threads;
+        sp.items_cells = std::max(1, H > 1 ? DZ_IMAX / H : DZ_IMAX * (threads / rowsP));
+    }
     sp.retry_list = ctx->d_retry;
     sp.big_list = ctx->d_big;
     sp.workspace = nullptr;
@@ -668,6 +660,7 @@ int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net_c, int32_t n, const i
     for (int d = 0; d < n; d++) {
         if (partition[d] < 1) return fail(ctx, CLR_ERR_ARG, "partition[%d] = %d: each dimension needs at least one block", d, partition[d]);
         in.part[d] = partition[d]; in.base[d] = tab;
+        in.stride[d] = (long long)std::min<long double>(total, 9.0e18L);
         tab += partition[d];
         total *= partition[d];
     }

@@ -1,0 +1,66 @@
+// deepz_types.cuh -- argument structures of deepz_kernel shared by the host code and the kernel units.
+#pragma once
+#include <cstddef>
+#include "common.cuh"
+
+struct DeepzInput {
+    int kind;                 // 0: box grid, 1: explicit zonotopes
+    int n;                    // rows of the input sets
+    long long N;              // cells of this call
+    long long cell_begin;     // box grid: id of the first cell in product order
+    int part[64];
+    int base[64];
+    long long stride[64];     // product of part[0..d-1]
+    const double* centers;    // device
+    const double* radii;      // device
+    const double* C;          // device, n x N
+    const long long* col_off; // device, N + 1
+    const double* G;          // device, n x col_off[N]
+};
+
+struct DeepzOutput {
+    double* out_lo;           // m_out x N or nullptr
+    double* out_hi;
+    double* hull_lo;          // m_out or nullptr (initialised to +inf / -inf by the host)
+    double* hull_hi;
+    int keep_cap;
+    int* keepN;               // N
+    double* keepC;            // m_out x N
+    double* keepG;            // m_out x keep_cap x N
+};
+
+struct DeepzSched {
+    int pass;                 // 0: main (adaptive tiles), 1: retry list (1 cell / tile), 2: big list (global store)
+    int tile_cells;           // fixed tile size (0 = adaptive)
+    int cap;                  // doubles per column-store buffer
+    int items_cells;          // max cells per tile from the relaxation item budget
+    long long* retry_list;
+    long long* big_list;
+    double* workspace;        // pass 2: gridDim.x * 2 * cap doubles
+};
+
+struct DeepzSmem {
+    int nCells, nCols, tileT, more;
+    long long firstIdx;
+    float peakNeed;
+    int sMaxP;
+    int colOff[2][CLR_TILE_CELLS_MAX + 1];    // double buffered: the relaxation reads the old layout while warp 0 publishes the new
+    long long cellId[CLR_TILE_CELLS_MAX];
+    unsigned mask[CLR_TILE_CELLS_MAX][CLR_MASK_WORDS];
+    unsigned centreMask[CLR_NCOL_MAX / 32];
+    unsigned deadMask[CLR_NCOL_MAX / 32];   // generators the reference's remove_zero_columns has dropped
+    double hlo[CLR_HULL_MAX], hhi[CLR_HULL_MAX];
+    unsigned long long sPin[CLR_MAX_LAYERS], sUnst[CLR_MAX_LAYERS], sNear;
+    DevLayer layers[CLR_DEV_MAX_LAYERS];
+    // ---- only allocated by the STATS instantiations (see dz_meta_bytes) ----
+    unsigned int cellNear[CLR_TILE_CELLS_MAX];
+    unsigned short cellPin[CLR_TILE_CELLS_MAX][CLR_MAX_LAYERS];
+    unsigned short cellUnst[CLR_TILE_CELLS_MAX][CLR_MAX_LAYERS];
+};
+__host__ __device__ inline size_t dz_meta_bytes(bool stats) {
+    size_t b = stats ? sizeof(DeepzSmem) : offsetof(DeepzSmem, cellNear);
+    return (b + 15) & ~(size_t)15;
+}
+
+#define DZ_IMAX 4        // relaxation items (cell, row) per thread
+#define DZ_THREADS 512   // 16 warps, always (4 per SM sub-partition: 128 registers per thread)

@@ -1,22 +1,13 @@
-"""Small driver for ncu: one device-resident DeepZ call on a slice of the C4 workload.
-
-    python profiles/prof_deepz.py <regime> <cells> [reps]
-"""
-import os
-import sys
-
+"""Tile-size sweep of the DeepZ main pass on a slice of the C4 workload (device-resident I/O)."""
+import os, sys
 import numpy as np
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import torch  # noqa: E402
-import clr_b200  # noqa: E402,F401
-from clr_b200 import runtime, workloads  # noqa: E402
-
+import torch
+import clr_b200
+from clr_b200 import runtime, workloads
 regime = sys.argv[1] if len(sys.argv) > 1 else "stable"
 cells = int(sys.argv[2]) if len(sys.argv) > 2 else 200000
-reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-tile = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 ctx = runtime.Context(0)
 net = workloads.synthetic_relu_net()
 grid = workloads.c4_grid(regime)
@@ -28,9 +19,10 @@ lo = torch.empty((cells, 1), dtype=torch.float64, device=dev)
 hi = torch.empty((cells, 1), dtype=torch.float64, device=dev)
 pp = runtime.PrePostArg(None, None)
 ctx.set_profiling(True)
-ctx.set_tile_cells(tile)
-for _ in range(reps):
-    ctx.deepz_boxgrid_dev(dn, 6, grid.partition, cc, rr, 400000, cells, pp, lo, hi)
-    ctx.synchronize()
-    print(ctx.last_pass_info())
+for T in [0, 1, 2, 3, 4, 6, 8, 10, 12, 13, 14, 16, 20, 24, 32]:
+    ctx.set_tile_cells(T)
+    for _ in range(2):
+        ctx.deepz_boxgrid_dev(dn, 6, grid.partition, cc, rr, 400000, cells, pp, lo, hi)
+        ctx.synchronize()
+    print(T, ctx.last_pass_info(), flush=True)
 ctx.close()
