@@ -35,6 +35,7 @@ struct Compiled {            // one (network, pre/post-processing) pair on the d
     int ksreg = 8;
     int warps = 8;
     int stored_width = 0;
+    int inplace = 1;
     int worst_cols_growth = 0;
 };
 
@@ -252,12 +253,10 @@ int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Com
         d.n = h.n; d.m = h.m;
         d.ksteps = (h.n + 3) / 4;
         d.rblocks = (h.m + 7) / 8;
-        d.pitch_in = l == 0 ? clr_pitch(n_in) : D.layer[l - 1].pitch_out;
-        d.pitch_out = clr_pitch(h.m);
         d.act = h.act; d.collapse = h.collapse; d.net_layer = h.net_layer;
         d.remove_zero = h.act != CLR_ACT_ID || h.project;
         D.max_rows = std::max(D.max_rows, h.m);
-        D.max_pitch = std::max(D.max_pitch, d.pitch_out);
+        D.max_pitch = std::max(D.max_pitch, clr_pitch(h.m));
         if (d.ksteps <= 32) maxKsReg = std::max(maxKsReg, d.ksteps);
         maxRB = std::max(maxRB, d.rblocks);
         // DMMA A fragments: [rb][ks][lane] = W[rb*8 + lane/4][ks*4 + lane%4]
@@ -281,12 +280,14 @@ int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Com
         image.insert(image.end(), h.b.begin(), h.b.end());
         P.Wcm[l] = d.Wcm; P.b[l] = d.bias; P.Wrm[l] = nullptr;
     }
+    for (int l = 0; l < D.L; l++) { D.layer[l].pitch_in = D.max_pitch; D.layer[l].pitch_out = D.max_pitch; }
     P.total_doubles = (int)image.size();
     if ((rc = upload(ctx, c, image, &P.image))) { free_compiled(c); return rc; }
     c->stored_width = ro_stored_width(P.dims, P.L);
     const int ks_opts[4] = {8, 16, 25, 32};
     c->ksreg = 32;
     for (int o = 0; o < 4; o++) if (maxKsReg <= ks_opts[o]) { c->ksreg = ks_opts[o]; break; }
+    c->inplace = maxRB <= DZ_THREADS / 32;   // every warp owns at most one row block
     c->warps = maxRB >= 16 ? 16 : maxRB * (16 / maxRB);
     if (c->warps < 4) c->warps = 4;
     {
@@ -403,15 +404,11 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     const int threads = DZ_THREADS;
     const size_t meta = dz_meta_bytes(want_stats);
     const size_t smem_total = (size_t)ctx->smem_optin;
-    if (smem_total < meta + 2 * 8 * 64) return fail(ctx, CLR_ERR_CUDA, "device has too little shared memory");
+    if (smem_total < meta + 8 * 1024) return fail(ctx, CLR_ERR_CUDA, "device has too little shared memory");
     DeepzSched sp{};
-    sp.cap = (int)((smem_total - meta) / 16);
+    sp.cap = (int)((smem_total - meta) / 8);
     sp.tile_cells = ctx->tile_cells;
-    {
-        const int rowsP = clr_pad4(D.max_rows);
-        const int H = (rowsP + threads - 1) / threads;
-        sp.items_cells = std::max(1, H > 1 ? DZ_IMAX / H : DZ_IMAX * (threads / rowsP));
-    }
+    sp.inplace = c->inplace;
     sp.retry_list = ctx->d_retry;
     sp.big_list = ctx->d_big;
     sp.workspace = nullptr;
@@ -420,10 +417,10 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     sp.pass = 0;
     ctx->pass_ms[0] = ctx->pass_ms[1] = ctx->pass_ms[2] = 0.f;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 16, c->dev, in, out, sp))) return rc;
+    if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 8, c->dev, in, out, sp))) return rc;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
-    if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 16, c->dev, in, out, sp))) return rc;
+    if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 8, c->dev, in, out, sp))) return rc;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     // how many cells did not fit in shared memory at all?
     CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -438,9 +435,10 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         const int wc = worst_cols(D, p0max);
         DeepzSched sg = sp;
         sg.pass = 2;
-        sg.cap = (wc + 8) * D.max_pitch;
+        const int stageW = std::max(clr_pad4(D.max_rows), 2 * D.n_in);
+        sg.cap = (wc + 8) * D.max_pitch * (c->inplace ? 1 : 2) + stageW + 64;
         int gridg = (int)std::min<unsigned long long>((unsigned long long)ctx->sms, ctx->h_state->n_big);
-        size_t need = sizeof(double) * (size_t)gridg * 2 * sg.cap;
+        size_t need = sizeof(double) * (size_t)gridg * sg.cap;
         if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, need))) return rc;
         sg.workspace = ctx->d_ws;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));

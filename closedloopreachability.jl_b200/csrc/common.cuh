@@ -9,7 +9,7 @@
 #define CLR_MAX_ROWS 512                          // widest layer supported (mask words below)
 #define CLR_MASK_WORDS (CLR_MAX_ROWS / 32)
 #define CLR_TILE_CELLS_MAX 64                     // cells per tile (smem metadata is sized for this)
-#define CLR_NCOL_MAX 4096                         // columns per tile
+#define CLR_NCOL_MAX 2048                         // columns per tile
 #define CLR_HULL_MAX 64                           // output dims with a per-CTA hull accumulator
 
 // ReachabilityBase.Comparison tolerances for Float64 (rtol = sqrt(eps), ztol = 10 eps, atol = 0)

@@ -4,27 +4,49 @@
 // controller_forward (src/solve.jl:210-218) with one persistent kernel:
 //
 //   * a CTA owns a TILE of cells; the tile's zonotopes ([centre | generators] per cell, all cells
-//     side by side) live in shared memory as one column store (column-major, conflict-free pitch);
+//     side by side) live in shared memory as ONE column store (column-major, one conflict-free pitch
+//     for the whole network) that every layer transforms IN PLACE;
 //   * per layer, W * [c | G] for all columns of the tile runs on the FP64 tensor pipe
 //     (mma.sync.m8n8k4.f64 -> SASS DMMA; tcgen05 has no FP64 kind): a warp owns 8 output rows,
-//     keeps their W fragments in registers and streams the columns as B fragments from smem;
+//     keeps their W fragments in registers and streams the columns as B fragments from smem.  The
+//     sweep goes over the column groups back to front; results are written to the columns' positions
+//     in the NEXT layout (cells only ever move right, making room for appended generators), and an
+//     mbarrier phase per column group keeps writers behind all readers;
+//   * generators appended by the previous relaxation are mu * e_i: their image under W is mu * W[:, i],
+//     so they never go through the tensor pipe -- they are materialised as scaled weight columns;
 //   * the interval bounds (sequential |.| row sums, same order as LazySets low/high), the
-//     ReLU / sigmoid / tanh relaxation, the row scaling and the append of the new generators
-//     are fused in the same kernel and never leave the SM;
+//     ReLU / sigmoid / tanh relaxation and the row scaling happen in place in the same kernel and never
+//     leave the SM; the appended generators are kept as (row mask, mu) until the next layer;
 //   * the output box (src/solve.jl:214-216, src/setops.jl:76-83), the hull over cells and the
 //     optional output zonotopes are written straight from smem.
 //
-// Tiles are handed out by an atomic cursor; the tile size adapts to the generator growth seen so
-// far; cells that overflow a tile are retried alone and, if a single cell does not fit in
-// shared memory, in a pass whose column store lives in a global (L2-resident) workspace.
+// Tiles are handed out by an atomic cursor (prefetched one tile ahead); the tile size adapts to the
+// generator growth seen so far; cells that overflow a tile are retried in smaller tiles and, if a
+// single cell does not fit in shared memory, in a pass whose column store lives in a global
+// (L2-resident) workspace.
 #pragma once
 #include "deepz_types.cuh"
-
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
+}
+
+// ---- mbarrier (shared memory barrier with phases): split arrive / wait for the in-place sweep -----------
+__device__ __forceinline__ unsigned dz_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dz_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(dz_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void dz_mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(dz_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void dz_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @!p bra W_%=;\n}\n" ::"r"(dz_smem_addr(bar)), "r"(parity)
+        : "memory");
 }
 
 __device__ __forceinline__ bool dz_approxzero(double x) { return fabs(x) <= CLR_ZTOL; }
@@ -56,8 +78,8 @@ __device__ __forceinline__ void atomicMaxD(double* addr, double v) {
 // ---------------------------------------------------------------------------------------------
 // Warp -> (row block, column part) mapping of the layer product.  16 warps sit on 4 SM sub-partitions
 // (warp w on w % 4); the DMMA rate is per sub-partition, so the row blocks are dealt such that the
-// sub-partitions get (nearly) the same number of DMMAs: with 13 row blocks (100 neurons) warps 0..11
-// own one row block each and warps 12..15 share the last one, a quarter of the columns each.
+// sub-partitions get the same number of DMMAs: with 13 row blocks (100 neurons) warps 0..11 own one
+// row block each and warps 12..15 share the last one, a quarter of the column groups each.
 // ---------------------------------------------------------------------------------------------
 struct DzMap { int rb0, rbStep, part, nParts; };
 __device__ __forceinline__ DzMap dz_map(int RB, int warp, int nWarps) {
@@ -83,104 +105,94 @@ __device__ __forceinline__ void dz_load_a(const DevLayer& L, int warp, int lane,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Layer product: Y[:, j] = W * X[:, j] for all nCols columns (bias is added by the relaxation, or
-// here on the centre columns for Id layers).  `a` holds the fragments of the warp's first row block.
+// Layer product.  Column j of X (current layout) goes to column colPos[j] of Y (next layout);
+// Y == X when `inplace` (then the groups are swept back to front under the mbarrier protocol).
+// Bias is added by the relaxation, or here on the centre columns for layers without one.
 // ---------------------------------------------------------------------------------------------
 template <int KSREG>
-__device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* __restrict__ X, double* __restrict__ Y,
-                                        int nCols, const unsigned* centreMask, bool addBias, int warp, int lane,
-                                        int nWarps, double (&a)[KSREG]) {
+__device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, double* Y, int P, int nCols,
+                                        const unsigned short* colPos, bool addBias, bool inplace,
+                                        unsigned long long* bars, unsigned (&phase)[2], int warp, int lane, int nWarps,
+                                        double (&a)[KSREG]) {
     constexpr int NB = 4;                       // column blocks (8 columns each) per group
     const int RB = L.rblocks, KS = L.ksteps;
     const int CG = (nCols + 8 * NB - 1) / (8 * NB);
-    const int pin = L.pitch_in, pout = L.pitch_out;
     const int rowsW = clr_pad4(L.m);            // rows written (pad rows of W are zero)
     const int qr = lane >> 2, qc = lane & 3;
     const DzMap mp = dz_map(RB, warp, nWarps);
-    for (int rb = mp.rb0; rb < RB; rb += mp.rbStep) {
-        const double* Af = L.Afrag + (size_t)rb * KS * 32 + lane;
+    const bool resident = KS <= KSREG;
+    // in place every warp walks all groups exactly once (it owns at most one row block); otherwise row blocks outermost
+    for (int rb = mp.rb0; rb < RB || (inplace && rb == mp.rb0); rb += mp.rbStep) {
+        const bool active = rb < RB;
+        const double* Af = L.Afrag + (size_t)(active ? rb : 0) * KS * 32 + lane;
         const int row = rb * 8 + qr;
-        const double bias = (addBias && row < L.m) ? __ldg(L.bias + row) : 0.0;
-        const bool resident = KS <= KSREG;
-        if (resident && rb != mp.rb0) {
+        const double bias = (addBias && active && row < L.m) ? __ldg(L.bias + row) : 0.0;
+        if (active && resident && rb != mp.rb0) {
 #pragma unroll
             for (int k = 0; k < KSREG; k++) a[k] = k < KS ? __ldg(Af + k * 32) : 0.0;
         }
-        for (int cg = mp.part; cg < CG; cg += mp.nParts) {
+        for (int cg = CG - 1; cg >= 0; cg--) {
+            const bool mine = active && (cg % mp.nParts) == mp.part;
             double d[NB][2];
 #pragma unroll
             for (int j = 0; j < NB; j++) { d[j][0] = 0.0; d[j][1] = 0.0; }
-            const double* xb = X + (cg * NB * 8 + qr) * pin + qc;
             const int nbAct = min(NB, (nCols - cg * NB * 8 + 7) >> 3);   // column blocks that hold real columns
-            if (resident) {
+            if (mine) {
+                const double* xb = X + (cg * NB * 8 + qr) * P + qc;
+                if (resident) {
 #pragma unroll
-                for (int k = 0; k < KSREG; k++) {
-                    if (k < KS) {
+                    for (int k = 0; k < KSREG; k++) {
+                        if (k < KS) {
+#pragma unroll
+                            for (int j = 0; j < NB; j++) {
+                                if (j < nbAct) {
+                                    double b = xb[j * 8 * P + k * 4];
+                                    dmma884(d[j][0], d[j][1], a[k], b);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < KS; k++) {      // wide-K layers: stream the A fragments
+                        double av = __ldg(Af + k * 32);
 #pragma unroll
                         for (int j = 0; j < NB; j++) {
                             if (j < nbAct) {
-                                double b = xb[j * 8 * pin + k * 4];
-                                dmma884(d[j][0], d[j][1], a[k], b);
+                                double b = xb[j * 8 * P + k * 4];
+                                dmma884(d[j][0], d[j][1], av, b);
                             }
                         }
                     }
                 }
-            } else {
-                // wide-K layers: stream the A fragments
-                for (int k = 0; k < KS; k++) {
-                    double av = __ldg(Af + k * 32);
-#pragma unroll
-                    for (int j = 0; j < NB; j++) {
-                        if (j < nbAct) {
-                            double b = xb[j * 8 * pin + k * 4];
-                            dmma884(d[j][0], d[j][1], av, b);
-                        }
-                    }
-                }
             }
-            if (row < rowsW) {
+            if (inplace) {
+                // everybody has read group cg (and all groups behind it): only then may its results, which land
+                // at or behind column 32 cg, be written
+                unsigned long long* bar = bars + (cg & 1);
+                __syncwarp();
+                if (lane == 0) dz_mbar_arrive(bar);
+                dz_mbar_wait(bar, phase[cg & 1]);
+                phase[cg & 1] ^= 1u;
+            }
+            if (mine && row < rowsW) {
 #pragma unroll
                 for (int j = 0; j < NB; j++) {
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        int col = cg * NB * 8 + j * 8 + qc * 2 + e;
+                        const int col = cg * NB * 8 + j * 8 + qc * 2 + e;
                         if (col < nCols) {
-                            double v = d[j][e];
-                            if (addBias && ((centreMask[col >> 5] >> (col & 31)) & 1u)) v += bias;
-                            Y[col * pout + row] = v;
+                            const unsigned pos = colPos[col];
+                            if (pos != 0xFFFFu) {
+                                double v = d[j][e];
+                                if (addBias && (pos & 0x8000u)) v += bias;
+                                Y[(pos & 0x7FFFu) * P + row] = v;
+                            }
                         }
                     }
                 }
             }
         }
     }
-}
-
-// remove_zero_columns bookkeeping: the reference drops all-zero generators after every non-Id
-// activation (and after a projection); columns are never physically removed here (a zero column
-// stays zero and contributes nothing), they are only marked so that generator counts, statistics
-// and fetched zonotopes agree with the reference.
-__device__ __forceinline__ void dz_mark_dead(DeepzSmem& S, const double* X, int pitch, int rows, int nCols,
-                                             int tid, int NT) {
-    for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) S.deadMask[i] = 0;
-    __syncthreads();
-    for (int col = tid; col < nCols; col += NT) {
-        if ((S.centreMask[col >> 5] >> (col & 31)) & 1u) continue;
-        bool any = false;
-        for (int r = 0; r < rows && !any; r++) any = X[(size_t)col * pitch + r] != 0.0;
-        if (!any) atomicOr(&S.deadMask[col >> 5], 1u << (col & 31));
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void dz_build_centre_mask(DeepzSmem& S, const int* colOff, int nCells, int tid, int NT) {
-    for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) S.centreMask[i] = 0;
-    __syncthreads();
-    if (tid < nCells) {
-        int cb = colOff[tid];
-        atomicOr(&S.centreMask[cb >> 5], 1u << (cb & 31));
-    }
-    __syncthreads();
 }
 
 __device__ __forceinline__ double dz_sigm(double x) { return 1.0 / (1.0 + exp(-x)); }
@@ -188,9 +200,9 @@ __device__ __forceinline__ double dz_sigm_p(double x) { double ex = exp(x); retu
 __device__ __forceinline__ double dz_tanh_p(double x) { double t = tanh(x); return 1.0 - t * t; }
 
 // Column layout of a tile from per-cell widths, computed redundantly by every warp (no serial
-// section, no barrier): lane i holds the widths of cells i and i + 32 and gets their offsets back;
-// `keep` = number of leading cells that fit into `cap` doubles at pitch `pm`, `total` their columns.
-__device__ __forceinline__ void dz_layout(int w0, int w1, int nCells, int pm, int cap, int lane, int& off0, int& off1,
+// section): lane i holds the widths of cells i and i + 32 and gets their offsets back;
+// `keep` = number of leading cells that fit into capCols columns, `total` their columns.
+__device__ __forceinline__ void dz_layout(int w0, int w1, int nCells, int capCols, int lane, int& off0, int& off1,
                                           int& keep, int& total) {
     int s0 = w0, s1 = w1;
 #pragma unroll
@@ -200,8 +212,8 @@ __device__ __forceinline__ void dz_layout(int w0, int w1, int nCells, int pm, in
         if (lane >= d) { s0 += t0; s1 += t1; }
     }
     s1 += __shfl_sync(0xffffffffu, s0, 31);
-    const bool f0 = lane < nCells && (long long)(s0 + 8) * pm <= cap && s0 <= CLR_NCOL_MAX;
-    const bool f1 = lane + 32 < nCells && (long long)(s1 + 8) * pm <= cap && s1 <= CLR_NCOL_MAX;
+    const bool f0 = lane < nCells && s0 + 8 <= capCols;
+    const bool f1 = lane + 32 < nCells && s1 + 8 <= capCols;
     keep = __popc(__ballot_sync(0xffffffffu, f0)) + __popc(__ballot_sync(0xffffffffu, f1));
     off0 = s0 - w0; off1 = s1 - w1;
     const int e0 = __shfl_sync(0xffffffffu, s0, (keep - 1) & 31);
@@ -231,6 +243,26 @@ __device__ __forceinline__ void dz_defer(const DeepzSched& sp, DevCallState* st,
     atomicAdd(&st->dropped, (unsigned long long)nd);
 }
 
+// remove_zero_columns bookkeeping: the reference drops all-zero generators after every non-Id
+// activation (and after a projection); columns are never physically removed here (a zero column
+// stays zero and contributes nothing), they are only marked so that generator counts, statistics
+// and fetched zonotopes agree with the reference.  Marks the used generator columns of the
+// current layout that are identically zero.
+__device__ __forceinline__ void dz_mark_dead(DeepzSmem& S, unsigned* dead, const int* colOff, const double* X, int P,
+                                             int rows, int nCells, int tid, int NT) {
+    for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) dead[i] = 0;
+    __syncthreads();
+    for (int ci = tid >> 5; ci < nCells; ci += NT >> 5) {
+        const int cb = colOff[ci], w = S.wUsed[ci];
+        for (int j = 1 + (tid & 31); j < w; j += 32) {
+            bool any = false;
+            for (int r = 0; r < rows && !any; r++) any = X[(cb + j) * P + r] != 0.0;
+            if (!any) atomicOr(&dead[(cb + j) >> 5], 1u << ((cb + j) & 31));
+        }
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------
 // The persistent tile kernel.
 // ---------------------------------------------------------------------------------------------
@@ -239,50 +271,49 @@ __global__ void __launch_bounds__(DZ_THREADS, 1)
 deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, DevCallState* st, DeepzSched sp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeepzSmem& S = *reinterpret_cast<DeepzSmem*>(smem_raw);
-    double* buf0;
-    double* buf1;
-    if (GLOBAL) {
-        buf0 = sp.workspace + (size_t)blockIdx.x * 2 * sp.cap;
-        buf1 = buf0 + sp.cap;
-    } else {
-        buf0 = reinterpret_cast<double*>(smem_raw + dz_meta_bytes(STATS));
-        buf1 = buf0 + sp.cap;
-    }
+    double* store = GLOBAL ? sp.workspace + (size_t)blockIdx.x * sp.cap
+                           : reinterpret_cast<double*>(smem_raw + dz_meta_bytes(STATS));
     const int tid = threadIdx.x, NT = DZ_THREADS;
     const int lane = tid & 31, warp = tid >> 5, nWarps = NT >> 5;
-    const int CAP = sp.cap;
     const int L = net->L;
+    const int P = net->max_pitch;                 // one column pitch for the whole network
     const int mOut = net->m_out;
+    const int n = in.n;
+    const bool inplace = sp.inplace != 0;
     const bool useHull = out.hull_lo != nullptr && mOut <= CLR_HULL_MAX;
     const bool needDead = STATS || out.keep_cap > 0;
+    const int stageW = max(clr_pad4(net->max_rows), 2 * n);   // doubles of staging per cell
 
-    // ---- one-time setup: layer descriptors to smem, accumulators, the first tile --------------------------
+    // ---- one-time setup: layer descriptors to smem, accumulators, barriers, the first tile ------------------
     for (int i = tid; i < L * (int)(sizeof(DevLayer) / sizeof(int)); i += NT) ((int*)S.layers)[i] = ((const int*)net->layer)[i];
     if (tid < CLR_MAX_LAYERS) { S.sPin[tid] = 0; S.sUnst[tid] = 0; }
     if (tid < CLR_HULL_MAX) { S.hlo[tid] = INFINITY; S.hhi[tid] = -INFINITY; }
     const unsigned long long total_units =
         sp.pass == 0 ? (unsigned long long)in.N : (sp.pass == 1 ? st->n_retry : st->n_big);
     unsigned long long* cursor = sp.pass == 0 ? &st->next_cell : (sp.pass == 1 ? &st->next_retry : &st->next_big);
+    const int tileMax = min(CLR_TILE_CELLS_MAX, max(1, (sp.cap / 8) / stageW));   // staging takes 1/8 of the store at most
     unsigned long long pfFirst = 0;   // thread 0: prefetched tile
     int pfT = 0;
     if (tid == 0) {
+        dz_mbar_init(&S.bar[0], nWarps);
+        dz_mbar_init(&S.bar[1], nWarps);
         int t0 = sp.tile_cells;
-        if (sp.pass != 0) t0 = 1;
-        else if (t0 <= 0) {
+        if (t0 <= 0) {
             int guessCols = in.kind == 0 ? in.n + 1 : 8;
-            t0 = CAP / ((guessCols * 2 + 8) * net->max_pitch);
+            t0 = (sp.cap / (inplace ? 1 : 2)) / ((guessCols * 2 + 8) * P);
+            if (sp.pass != 0) t0 = max(1, t0 / 4);
             unsigned long long fair = (total_units + 2ull * gridDim.x - 1) / (2ull * gridDim.x);
             if ((unsigned long long)t0 > fair) t0 = (int)(fair < 1 ? 1 : fair);
         }
-        t0 = max(1, min(t0, min(CLR_TILE_CELLS_MAX, sp.items_cells)));
+        if (sp.pass == 2) t0 = 1;
+        t0 = max(1, min(t0, tileMax));
         S.tileT = t0;
         S.sNear = 0; S.sMaxP = 0;
         pfT = t0;
         pfFirst = atomicAdd(cursor, (unsigned long long)pfT);
     }
     __syncthreads();
-    bool needCentre = needDead;
-    for (int l = 0; l < L; l++) needCentre = needCentre || (S.layers[l].act == CLR_ACT_ID && !S.layers[l].collapse);
+    unsigned phase[2] = {0u, 0u};
     double a[KSREG];
 #pragma unroll
     for (int k = 0; k < KSREG; k++) a[k] = 0.0;
@@ -299,7 +330,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             S.peakNeed = 0.f;
             if (nc > 0) {
                 int T = S.tileT;
-                if (sp.pass == 0 && sp.tile_cells <= 0) {
+                if (sp.tile_cells <= 0 && sp.pass != 2) {
                     unsigned long long seen = pfFirst + (unsigned long long)nc;
                     unsigned long long rem = seen < total_units ? total_units - seen : 0;
                     unsigned long long fair = (rem + 2ull * gridDim.x - 1) / (2ull * gridDim.x);
@@ -313,23 +344,27 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         __syncthreads();
         if (!S.more) break;
         int nCells = S.nCells;
+        // store geometry of this tile: [columns ... | staging (nCells x stageW)]
+        const int stageOff = sp.cap - nCells * stageW;
+        double* stage = store + stageOff;
+        const int region = inplace ? stageOff : stageOff / 2;
+        const int capCols = min(region / P, CLR_NCOL_MAX);
+        double* cur = store;
+        double* oth = inplace ? store : store + region;
         if (tid < nCells) {
             long long idx = S.firstIdx + tid;
             S.cellId[tid] = sp.pass == 0 ? idx : (sp.pass == 1 ? sp.retry_list[idx] : sp.big_list[idx]);
             if (STATS) S.cellNear[tid] = 0;
         }
-        if (needDead) for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) S.deadMask[i] = 0;
+        for (int i = tid; i < nCells * CLR_MASK_WORDS; i += NT) (&S.mask[0][0])[i] = 0;
+        if (needDead) for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) { S.deadMask[0][i] = 0; S.deadMask[1][i] = 0; }
         __syncthreads();
 
         // ---- input zonotopes -> column store -------------------------------------------------------------------
-        const int n = in.n;
-        const int pin0 = S.layers[0].pitch_in;
-        int flip = 0;
+        int flip = 0, flipD = 0;
         int nCols;
-        double* cur = buf0;
-        double* oth = buf1;
-        double* tmpC = oth;                       // box grid: per-cell centre / radius scratch in the free buffer
-        double* tmpR = oth + nCells * n;
+        double* tmpC = stage;                     // box grid: per-cell centre / radius scratch
+        double* tmpR = stage + nCells * n;
         if (in.kind == 0) {
             for (int it = tid; it < nCells * n; it += NT) {
                 const int ci = it / n, d = it - ci * n;
@@ -359,14 +394,17 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 }
             }
             int off0, off1, keep, total;
-            dz_layout(w[0], w[1], nCells, max(pin0, S.layers[0].pitch_out), CAP, lane, off0, off1, keep, total);
+            const int wu0 = w[0], wu1 = w[1];
+            if (S.layers[0].collapse) { if (lane < nCells) w[0] = max(w[0], 2); if (lane + 32 < nCells) w[1] = max(w[1], 2); }
+            dz_layout(w[0], w[1], nCells, capCols, lane, off0, off1, keep, total);
             if (warp == 0) {
-                if (lane < keep) S.colOff[0][lane] = off0;
-                if (lane + 32 < keep) S.colOff[0][lane + 32] = off1;
+                // with no pending generators the next layout equals the current one
+                if (lane < keep) { S.colOff[0][lane] = off0; S.colOff[1][lane] = off0; S.wUsed[lane] = (unsigned short)wu0; }
+                if (lane + 32 < keep) { S.colOff[0][lane + 32] = off1; S.colOff[1][lane + 32] = off1; S.wUsed[lane + 32] = (unsigned short)wu1; }
                 if (lane == 0) {
-                    S.colOff[0][keep] = total;
+                    S.colOff[0][keep] = total; S.colOff[1][keep] = total;
                     if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
-                    if (keep > 0) S.peakNeed = (float)((total + 8) * max(pin0, S.layers[0].pitch_out)) / (float)keep;
+                    if (keep > 0) S.peakNeed = (float)(total + 8) / (float)keep;
                 }
             }
             nCells = keep;
@@ -380,236 +418,258 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             if (in.kind == 0) {
                 for (int it = tid; it < nCells * rows4; it += NT) {
                     const int ci = it / rows4, d = it - ci * rows4;
-                    const int cb = colOff[ci], p = colOff[ci + 1] - cb - 1;
+                    const int cb = colOff[ci], p = S.wUsed[ci] - 1;
                     double c = 0.0, r = 0.0;
                     int rank = 0;
                     if (d < n) {
                         c = tmpC[ci * n + d]; r = tmpR[ci * n + d];
                         for (int dd = 0; dd < d; dd++) rank += tmpR[ci * n + dd] != 0.0;
                     }
-                    cur[cb * pin0 + d] = c;
-                    for (int j = 0; j < p; j++) cur[(cb + 1 + j) * pin0 + d] = (r != 0.0 && j == rank) ? r : 0.0;
+                    cur[cb * P + d] = c;
+                    for (int j = 0; j < p; j++) cur[(cb + 1 + j) * P + d] = (r != 0.0 && j == rank) ? r : 0.0;
                 }
             } else {
                 for (int it = tid; it < nCells * rows4; it += NT) {
                     const int ci = it / rows4, d = it - ci * rows4;
-                    const int cb = colOff[ci], p = colOff[ci + 1] - cb - 1;
+                    const int cb = colOff[ci], p = S.wUsed[ci] - 1;
                     const long long cell = S.cellId[ci];
                     const long long go = in.col_off[cell];
-                    cur[cb * pin0 + d] = d < n ? in.C[cell * n + d] : 0.0;
-                    for (int j = 0; j < p; j++) cur[(cb + 1 + j) * pin0 + d] = d < n ? in.G[(go + j) * n + d] : 0.0;
+                    cur[cb * P + d] = d < n ? in.C[cell * n + d] : 0.0;
+                    for (int j = 0; j < p; j++) cur[(cb + 1 + j) * P + d] = d < n ? in.G[(go + j) * n + d] : 0.0;
                 }
             }
-            if (needCentre) dz_build_centre_mask(S, colOff, nCells, tid, NT);
-            __syncthreads();   // input store complete
+            for (int ci = warp; ci < nCells; ci += nWarps) {
+                const int cb = colOff[ci], w = S.wUsed[ci], wa = colOff[ci + 1] - cb;
+                for (int j = lane; j < wa; j += 32)
+                    S.colPos[cb + j] = j < w ? (unsigned short)((cb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
+            }
+            __syncthreads();   // input store and position table complete
         }
 
         // ---- layers ------------------------------------------------------------------------------------------------
+        // invariant at the top: data in layout colOff[flip] (wUsed columns per cell), generators appended by the previous
+        // relaxation pending in mask / stage, next layout in colOff[flip ^ 1], colPos maps current -> next columns
         bool tileDead = false;
         for (int l = 0; l < L; l++) {
             const DevLayer& Ly = S.layers[l];
+            const int* offNxt = S.colOff[flip ^ 1];
             if (STATS && Ly.net_layer >= 0 && tid < nCells) {
-                // generator columns entering this layer, as the reference counts them
-                const int* colOff = S.colOff[flip];
-                int cb = colOff[tid], p = colOff[tid + 1] - cb - 1, nz = 0;
-                for (int j = 1; j <= p; j++) nz += !((S.deadMask[(cb + j) >> 5] >> ((cb + j) & 31)) & 1u);
+                // generators entering this layer, as the reference counts them
+                const int cb = S.colOff[flip][tid], w = S.wUsed[tid];
+                int nz = 0;
+                for (int j = 1; j < w; j++) nz += !((S.deadMask[flipD][(cb + j) >> 5] >> ((cb + j) & 31)) & 1u);
+                for (int ww = 0; ww < CLR_MASK_WORDS; ww++) nz += __popc(S.mask[tid][ww]);
                 S.cellPin[tid][Ly.net_layer] = (unsigned short)nz;
                 S.cellUnst[tid][Ly.net_layer] = 0;
             }
             const int act = Ly.act, collapse = Ly.collapse;
             const bool relax = !(act == CLR_ACT_ID && !collapse);
-            dz_gemm<KSREG>(Ly, cur, oth, nCols, S.centreMask, !relax, warp, lane, nWarps, a);
-            // the masks were last read by the previous relaxation, which ended with a barrier
-            for (int i = tid; i < nCells * CLR_MASK_WORDS; i += NT) (&S.mask[0][0])[i] = 0;
+            const int m = Ly.m, rowsP = clr_pad4(m);
+            dz_gemm<KSREG>(Ly, cur, oth, P, nCols, S.colPos, !relax, inplace, S.bar, phase, warp, lane, nWarps, a);
             // weights of the next layer (or of the first layer for the next tile) while the relaxation runs
             dz_load_a<KSREG>(S.layers[l + 1 < L ? l + 1 : 0], warp, lane, nWarps, a);
-            __syncthreads();
-            { double* t = cur; cur = oth; oth = t; }
-            if (!relax) {
-                if (needDead && Ly.remove_zero) dz_mark_dead(S, cur, Ly.pitch_out, Ly.m, nCols, tid, NT);
-                continue;
-            }
-
-            // ---- relaxation pass 1: bounds, lambda, mu; thread = (cell slot, row) ---------------------------------------
-            const int P = Ly.pitch_out, m = Ly.m, rowsP = clr_pad4(m);
-            const int H = (rowsP + NT - 1) / NT;      // row passes (2 only for layers wider than the CTA)
-            const int G = H > 1 ? 1 : NT / rowsP;     // cell slots processed side by side
-            const int slot = H > 1 ? 0 : tid / rowsP, r0 = tid - slot * rowsP;
-            const bool slotActive = slot < G;
-            const int* colOff = S.colOff[flip];
-            double lam[DZ_IMAX], mu[DZ_IMAX];
-#pragma unroll
-            for (int q = 0; q < DZ_IMAX; q++) {
-                const int ci = slot + (H > 1 ? q >> 1 : q) * G;
-                const int r = H > 1 ? r0 + (q & 1) * NT : r0;
-                lam[q] = 0.0; mu[q] = 0.0;
-                if (slotActive && ci < nCells && r < m) {
-                    const double bias = __ldg(Ly.bias + r);
-                    int cb = colOff[ci], p = colOff[ci + 1] - cb - 1;
-                    double* y = cur + cb * P + r;
-                    double c = y[0] + bias, lo, hi, rad = 0.0;
-                    if (collapse) {
-                        for (int j = 1; j <= p; j++) rad += fabs(y[j * P]);
-                        lo = c - rad; hi = c + rad;
-                    } else {
-                        lo = c; hi = c;
-                        for (int j = 1; j <= p; j++) { double av = fabs(y[j * P]); lo -= av; hi += av; }
+            __syncthreads();   // all columns of the current layout consumed and moved
+            // pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i]
+            if (l > 0) {
+                for (int ci = warp; ci < nCells; ci += nWarps) {
+                    int col = offNxt[ci] + S.wUsed[ci];
+                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) {
+                        unsigned bits = S.mask[ci][ww];
+                        while (bits) {
+                            const int i = ww * 32 + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const double mu = stage[ci * stageW + i];
+                            const double* wc = Ly.Wcm + (size_t)i * m;
+                            for (int r = lane; r < rowsP; r += 32) {
+                                double v = r < m ? mu * __ldg(wc + r) : 0.0;
+                                oth[col * P + r] = v;
+                            }
+                            col++;
+                        }
                     }
-                    bool unst = false;
-                    double cn = c, la = 1.0, mm = 0.0;
-                    if (act == CLR_ACT_RELU) {
-                        if (STATS && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
-                        if (dz_leq(lo, 0.0)) {
-                            if (dz_leq(hi, 0.0)) { cn = 0.0; la = 0.0; }
+                }
+                __syncthreads();
+                if (tid < nCells) {
+                    int u = 0;
+                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) { u += __popc(S.mask[tid][ww]); S.mask[tid][ww] = 0; }
+                    S.wUsed[tid] = (unsigned short)(S.wUsed[tid] + u);
+                }
+            }
+            if (needDead) {
+                // dead marks follow their columns to the new positions
+                unsigned* dOld = S.deadMask[flipD];
+                unsigned* dNew = S.deadMask[flipD ^ 1];
+                for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) dNew[i] = 0;
+                __syncthreads();
+                for (int col = tid; col < nCols; col += NT) {
+                    const unsigned pos = S.colPos[col];
+                    if (pos != 0xFFFFu && ((dOld[col >> 5] >> (col & 31)) & 1u)) atomicOr(&dNew[(pos & 0x7FFFu) >> 5], 1u << (pos & 31));
+                }
+                flipD ^= 1;
+            }
+            { double* t = cur; cur = oth; oth = t; }
+            flip ^= 1;
+            __syncthreads();   // layout flipped: data in colOff[flip], wUsed updated, masks clear
+            const int* colOff = S.colOff[flip];
+            nCols = colOff[nCells];
+            // ---- relaxation: bounds, lambda, mu, rows scaled in place; thread = (cell slot, row) ------------------------
+            if (relax) {
+                const int G = NT / rowsP;                 // cell slots processed side by side
+                const int slot = tid / rowsP, r = tid - slot * rowsP;
+                if (slot < G && r < m) {
+                    const double bias = __ldg(Ly.bias + r);
+                    for (int ci = slot; ci < nCells; ci += G) {
+                        const int cb = colOff[ci], w = S.wUsed[ci];
+                        double* y = cur + cb * P + r;
+                        double c = y[0] + bias, lo, hi, rad = 0.0;
+                        if (collapse) {
+                            for (int j = 1; j < w; j++) rad += fabs(y[j * P]);
+                            lo = c - rad; hi = c + rad;
+                        } else {
+                            lo = c; hi = c;
+                            for (int j = 1; j < w; j++) { double av = fabs(y[j * P]); lo -= av; hi += av; }
+                        }
+                        bool unst = false;
+                        double cn = c, la = 1.0, mm = 0.0;
+                        if (act == CLR_ACT_RELU) {
+                            if (STATS && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
+                            if (dz_leq(lo, 0.0)) {
+                                if (dz_leq(hi, 0.0)) { cn = 0.0; la = 0.0; }
+                                else {
+                                    la = hi / (hi - lo);
+                                    mm = -la * lo / 2;
+                                    cn = c * la + mm;
+                                    unst = true;
+                                }
+                            }
+                        } else if (act == CLR_ACT_SIGMOID || act == CLR_ACT_TANH) {
+                            double ly = act == CLR_ACT_SIGMOID ? dz_sigm(lo) : tanh(lo);
+                            double uy = act == CLR_ACT_SIGMOID ? dz_sigm(hi) : tanh(hi);
+                            if (dz_approx(lo, hi)) { cn = uy; la = 0.0; }
                             else {
-                                la = hi / (hi - lo);
-                                mm = -la * lo / 2;
-                                cn = c * la + mm;
+                                double dl = act == CLR_ACT_SIGMOID ? dz_sigm_p(lo) : dz_tanh_p(lo);
+                                double du = act == CLR_ACT_SIGMOID ? dz_sigm_p(hi) : dz_tanh_p(hi);
+                                la = dl < du ? dl : du;
+                                double mu1 = (uy + ly - la * (hi + lo)) / 2;
+                                mm = (uy - ly - la * (hi - lo)) / 2;
+                                cn = c * la + mu1;
                                 unst = true;
                             }
                         }
-                    } else if (act == CLR_ACT_SIGMOID || act == CLR_ACT_TANH) {
-                        double ly = act == CLR_ACT_SIGMOID ? dz_sigm(lo) : tanh(lo);
-                        double uy = act == CLR_ACT_SIGMOID ? dz_sigm(hi) : tanh(hi);
-                        if (dz_approx(lo, hi)) { cn = uy; la = 0.0; }
-                        else {
-                            double dl = act == CLR_ACT_SIGMOID ? dz_sigm_p(lo) : dz_tanh_p(lo);
-                            double du = act == CLR_ACT_SIGMOID ? dz_sigm_p(hi) : dz_tanh_p(hi);
-                            la = dl < du ? dl : du;
-                            double mu1 = (uy + ly - la * (hi + lo)) / 2;
-                            mm = (uy - ly - la * (hi - lo)) / 2;
-                            cn = c * la + mu1;
-                            unst = true;
+                        y[0] = cn;
+                        if (collapse) y[P] = la * rad;       // LazySets' one-row linear_map: a single generator
+                        else if (la != 1.0) { for (int j = 1; j < w; j++) y[j * P] = y[j * P] * la; }
+                        if (unst) {
+                            stage[ci * stageW + r] = mm;
+                            atomicOr(&S.mask[ci][r >> 5], 1u << (r & 31));
                         }
                     }
-                    lam[q] = collapse ? la * rad : la;   // collapse: the single generator, already scaled
-                    mu[q] = mm;
-                    y[0] = cn;                            // the new centre waits in place for pass 2
-                    if (unst) atomicOr(&S.mask[ci][r >> 5], 1u << (r & 31));
                 }
+                __syncthreads();
             }
-            __syncthreads();
-            // ---- new layout (every warp computes it; warp 0 publishes it) -------------------------------------------------
-            int off0, off1, keep, total;
+            // ---- next layout (every warp computes it; warp 0 publishes it) and the position table -----------------------
             {
-                int w[2] = {0, 0};
+                int off0, off1, keep, total;
+                int w[2] = {0, 0}, wu[2] = {0, 0};
                 const int mw = (m + 31) >> 5;
+                const int minW = (l + 1 < L && S.layers[l + 1].collapse) ? 2 : 1;   // a one-row map writes [c, r]
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int ci = lane + 32 * h;
                     if (ci < nCells) {
                         int u = 0;
                         for (int ww = 0; ww < mw; ww++) u += __popc(S.mask[ci][ww]);
-                        const int p = colOff[ci + 1] - colOff[ci] - 1;
-                        w[h] = 1 + (collapse ? 1 : p) + u;
+                        wu[h] = collapse ? 2 : S.wUsed[ci];
+                        w[h] = max(max(colOff[ci + 1] - colOff[ci], wu[h] + u), minW);   // cells never shrink: they only move right
                         if (STATS && warp == 0 && Ly.net_layer >= 0) S.cellUnst[ci][Ly.net_layer] = (unsigned short)u;
                     }
                 }
-                const int pm = l + 1 < L ? max(P, S.layers[l + 1].pitch_out) : P;
-                dz_layout(w[0], w[1], nCells, pm, CAP, lane, off0, off1, keep, total);
+                dz_layout(w[0], w[1], nCells, capCols, lane, off0, off1, keep, total);
+                int* cn = S.colOff[flip ^ 1];
                 if (warp == 0) {
-                    int* cn = S.colOff[flip ^ 1];
                     if (lane < keep) cn[lane] = off0;
                     if (lane + 32 < keep) cn[lane + 32] = off1;
                     if (lane == 0) {
                         cn[keep] = total;
                         if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
-                        if (keep > 0) S.peakNeed = fmaxf(S.peakNeed, (float)((total + 8) * pm) / (float)keep);
+                        if (keep > 0) S.peakNeed = fmaxf(S.peakNeed, (float)(total + 8) / (float)keep);
                     }
                 }
-            }
-            // ---- relaxation pass 2: scale rows, append generators, move to the new layout --------------------------------
-#pragma unroll
-            for (int q = 0; q < DZ_IMAX; q++) {
-                const int ci = slot + (H > 1 ? q >> 1 : q) * G;
-                const int r = H > 1 ? r0 + (q & 1) * NT : r0;
-                const int cs = min(ci, CLR_TILE_CELLS_MAX - 1);
-                const int nbA = __shfl_sync(0xffffffffu, off0, cs & 31);
-                const int nbB = __shfl_sync(0xffffffffu, off1, cs & 31);
-                const int nb = cs < 32 ? nbA : nbB;
-                if (slotActive && ci < keep && r < rowsP) {
-                    const int cb = colOff[ci], p = colOff[ci + 1] - cb - 1;
-                    const unsigned mwv = r < m ? S.mask[ci][r >> 5] : 0u;
-                    int u = 0;
-                    for (int ww = 0; ww < ((m + 31) >> 5); ww++) u += __popc(S.mask[ci][ww]);
-                    const double* y = cur + cb * P + r;
-                    double* z = oth + nb * P + r;
-                    if (r >= m) {
-                        const int wtot = 1 + (collapse ? 1 : p) + u;
-                        for (int j = 0; j < wtot; j++) z[j * P] = 0.0;
-                    } else {
-                        z[0] = y[0];
-                        int pk;
-                        if (collapse) { z[P] = lam[q]; pk = 1; }
-                        else {
-                            const double la = lam[q];
-                            for (int j = 1; j <= p; j++) z[j * P] = y[j * P] * la;
-                            pk = p;
-                        }
-                        if (u > 0) {
-                            const bool unst = (mwv >> (r & 31)) & 1u;
-                            int rank = __popc(mwv & ((1u << (r & 31)) - 1u));
-                            for (int ww = 0; ww < (r >> 5); ww++) rank += __popc(S.mask[ci][ww]);
-                            for (int k = 0; k < u; k++) z[(1 + pk + k) * P] = (unst && k == rank) ? mu[q] : 0.0;
-                        }
-                    }
+                // position table: cells dealt to the warps, lanes over a cell's columns
+                for (int ci = warp; ci < keep; ci += nWarps) {
+                    const int nb = ci < 32 ? __shfl_sync(0xffffffffu, off0, ci & 31) : __shfl_sync(0xffffffffu, off1, ci & 31);
+                    const int wuse = ci < 32 ? __shfl_sync(0xffffffffu, wu[0], ci & 31) : __shfl_sync(0xffffffffu, wu[1], ci & 31);
+                    const int cb = colOff[ci], wa = colOff[ci + 1] - cb;
+                    for (int j = lane; j < wa; j += 32)
+                        S.colPos[cb + j] = j < wuse ? (unsigned short)((nb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
                 }
+                if (collapse && warp == 1) {
+                    if (lane < keep) S.wUsed[lane] = 2;
+                    if (lane + 32 < keep) S.wUsed[lane + 32] = 2;
+                }
+                nCells = keep;
             }
-            __syncthreads();
-            { double* t = cur; cur = oth; oth = t; }
-            flip ^= 1;
-            nCells = keep;
-            nCols = total;
             if (nCells == 0) {
                 tileDead = true;
                 dz_load_a<KSREG>(S.layers[0], warp, lane, nWarps, a);   // the next tile starts at layer 0 again
+                __syncthreads();
                 break;
             }
-            if (needCentre) dz_build_centre_mask(S, S.colOff[flip], nCells, tid, NT);
+            nCols = colOff[nCells];          // columns of the current layout that the next product reads
+            __syncthreads();
             if (needDead) {
-                if (Ly.remove_zero) dz_mark_dead(S, cur, P, m, nCols, tid, NT);
-                else { for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) S.deadMask[i] = 0; }
+                if (Ly.remove_zero) dz_mark_dead(S, S.deadMask[flipD], colOff, cur, P, m, nCells, tid, NT);
+                else if (relax) { for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) S.deadMask[flipD][i] = 0; __syncthreads(); }
             }
         }
-        __syncthreads();
         if (tileDead) continue;
 
         // ---- outputs ---------------------------------------------------------------------------------------------------
         {
-            const int P = S.layers[L - 1].pitch_out;
             const int* colOff = S.colOff[flip];
-            // ranks of the surviving output generators (remove_zero_columns), in the free buffer
-            unsigned short* colRank = reinterpret_cast<unsigned short*>(oth);
+            const unsigned* dead = S.deadMask[flipD];
+            // ranks of the surviving output generators (remove_zero_columns); the position table is free now
+            unsigned short* colRank = S.colPos;
+            int* rank0 = S.colOff[flip ^ 1];              // rank of a cell's first pending generator
             if (needDead) {
                 if (tid < nCells) {
-                    int cb = colOff[tid], p = colOff[tid + 1] - cb - 1, k = 0;
+                    const int cb = colOff[tid], w = S.wUsed[tid];
+                    int k = 0;
                     colRank[cb] = 0xFFFF;
-                    for (int j = 1; j <= p; j++) {
-                        const bool dead = (S.deadMask[(cb + j) >> 5] >> ((cb + j) & 31)) & 1u;
-                        colRank[cb + j] = dead ? (unsigned short)0xFFFF : (unsigned short)(k++);
+                    for (int j = 1; j < w; j++) {
+                        const bool dd = (dead[(cb + j) >> 5] >> ((cb + j) & 31)) & 1u;
+                        colRank[cb + j] = dd ? (unsigned short)0xFFFF : (unsigned short)(k++);
                     }
-                    if (STATS) atomicMax(&S.sMaxP, k);
+                    int u = 0;
+                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[tid][ww]);
+                    rank0[tid] = k;
+                    if (STATS) atomicMax(&S.sMaxP, k + u);
                     if (out.keep_cap > 0) {
-                        out.keepN[S.cellId[tid]] = k;
-                        if (k > out.keep_cap) atomicCAS(&st->error, 0, (int)CLR_ERR_CAPACITY);
+                        out.keepN[S.cellId[tid]] = k + u;
+                        if (k + u > out.keep_cap) atomicCAS(&st->error, 0, (int)CLR_ERR_CAPACITY);
                     }
                 }
                 __syncthreads();
             }
             for (int it = tid; it < nCells * mOut; it += NT) {
-                int ci = it / mOut, r = it - ci * mOut;
-                int cb = colOff[ci], p = colOff[ci + 1] - cb - 1;
-                const double* y = cur + (size_t)cb * P + r;
+                const int ci = it / mOut, r = it - ci * mOut;
+                const int cb = colOff[ci], w = S.wUsed[ci];
+                const double* y = cur + cb * P + r;
+                const unsigned mwv = S.mask[ci][r >> 5];
+                const bool pend = (mwv >> (r & 31)) & 1u;     // this row's own appended generator mu * e_r
+                const double mu = pend ? stage[ci * stageW + r] : 0.0;
                 double c = y[0], lo, hi;
                 if (mOut == 1) {
                     lo = c; hi = c;
-                    for (int j = 1; j <= p; j++) { double av = fabs(y[(size_t)j * P]); lo -= av; hi += av; }
+                    for (int j = 1; j < w; j++) { double av = fabs(y[j * P]); lo -= av; hi += av; }
+                    if (pend) { lo -= fabs(mu); hi += fabs(mu); }
                 } else {
                     double rad = 0.0;
-                    for (int j = 1; j <= p; j++) rad += fabs(y[(size_t)j * P]);
+                    for (int j = 1; j < w; j++) rad += fabs(y[j * P]);
+                    if (pend) rad += fabs(mu);
                     lo = c - rad; hi = c + rad;
                 }
-                long long cell = S.cellId[ci];
+                const long long cell = S.cellId[ci];
                 if (out.out_lo) { out.out_lo[cell * mOut + r] = lo; out.out_hi[cell * mOut + r] = hi; }
                 if (out.hull_lo) {
                     if (useHull) { atomicMinD(&S.hlo[r], lo); atomicMaxD(&S.hhi[r], hi); }
@@ -618,10 +678,16 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 if (out.keep_cap > 0) {
                     out.keepC[cell * mOut + r] = c;
                     double* g = out.keepG + (size_t)cell * out.keep_cap * mOut + r;
-                    for (int j = 1; j <= p; j++) {
-                        unsigned short k = colRank[cb + j];
-                        if (k != 0xFFFF && k < out.keep_cap) g[(size_t)k * mOut] = y[(size_t)j * P];
+                    for (int j = 1; j < w; j++) {
+                        const unsigned short k = colRank[cb + j];
+                        if (k != 0xFFFF && k < out.keep_cap) g[(size_t)k * mOut] = y[j * P];
                     }
+                    int k0 = rank0[ci], u = 0;
+                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[ci][ww]);
+                    int rank = __popc(mwv & ((1u << (r & 31)) - 1u));
+                    for (int ww = 0; ww < (r >> 5); ww++) rank += __popc(S.mask[ci][ww]);
+                    for (int k = 0; k < u; k++)
+                        if (k0 + k < out.keep_cap) g[(size_t)(k0 + k) * mOut] = (pend && k == rank) ? mu : 0.0;
                 }
             }
             if (STATS) {
@@ -640,10 +706,12 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         }
         // ---- adapt the tile size to the growth just seen ---------------------------------------------------------------
         if (tid == 0) {
-            if (sp.pass == 0 && sp.tile_cells <= 0) {
-                float need = S.peakNeed * 1.0625f + 1.f;
-                int T = (int)((float)CAP / need);
-                S.tileT = max(1, min(T, min(CLR_TILE_CELLS_MAX, sp.items_cells)));
+            if (sp.tile_cells <= 0 && sp.pass != 2) {
+                const float margin = sp.pass == 0 ? 1.0625f : 1.5f;
+                // columns and staging both scale with the number of cells
+                const float perCell = S.peakNeed * margin * (float)P * (inplace ? 1.f : 2.f) + (float)stageW;
+                int T = (int)((float)(sp.cap - 16 * P) / perCell);
+                S.tileT = max(1, min(T, tileMax));
             }
             if (STATS) atomicAdd(&st->tiles, 1ull);
         }

@@ -30,25 +30,27 @@ struct DeepzOutput {
 };
 
 struct DeepzSched {
-    int pass;                 // 0: main (adaptive tiles), 1: retry list (1 cell / tile), 2: big list (global store)
+    int pass;                 // 0: main (adaptive tiles), 1: retry list, 2: big list (column store in global memory)
     int tile_cells;           // fixed tile size (0 = adaptive)
-    int cap;                  // doubles per column-store buffer
-    int items_cells;          // max cells per tile from the relaxation item budget
+    int cap;                  // doubles of column store (+ staging) per CTA
+    int inplace;              // 1: layer products run in place (every warp owns at most one row block)
     long long* retry_list;
     long long* big_list;
-    double* workspace;        // pass 2: gridDim.x * 2 * cap doubles
+    double* workspace;        // pass 2: gridDim.x * cap doubles
 };
 
 struct DeepzSmem {
-    int nCells, nCols, tileT, more;
+    unsigned long long bar[2];                // mbarriers of the in-place layer product (one phase per column group)
+    int nCells, tileT, more;
+    int sMaxP;
     long long firstIdx;
     float peakNeed;
-    int sMaxP;
-    int colOff[2][CLR_TILE_CELLS_MAX + 1];    // double buffered: the relaxation reads the old layout while warp 0 publishes the new
+    int colOff[2][CLR_TILE_CELLS_MAX + 1];    // cell offsets of the current and of the next layout
+    unsigned short wUsed[CLR_TILE_CELLS_MAX]; // columns of a cell that hold data (centre + generators)
     long long cellId[CLR_TILE_CELLS_MAX];
-    unsigned mask[CLR_TILE_CELLS_MAX][CLR_MASK_WORDS];
-    unsigned centreMask[CLR_NCOL_MAX / 32];
-    unsigned deadMask[CLR_NCOL_MAX / 32];   // generators the reference's remove_zero_columns has dropped
+    unsigned mask[CLR_TILE_CELLS_MAX][CLR_MASK_WORDS];   // rows whose relaxation appended a generator (pending: mu in the staging area)
+    unsigned short colPos[CLR_NCOL_MAX];      // column of the current layout -> column of the next one (0x8000: centre, 0xFFFF: unused)
+    unsigned deadMask[2][CLR_NCOL_MAX / 32];  // generators the reference's remove_zero_columns has dropped
     double hlo[CLR_HULL_MAX], hhi[CLR_HULL_MAX];
     unsigned long long sPin[CLR_MAX_LAYERS], sUnst[CLR_MAX_LAYERS], sNear;
     DevLayer layers[CLR_DEV_MAX_LAYERS];
@@ -62,5 +64,4 @@ __host__ __device__ inline size_t dz_meta_bytes(bool stats) {
     return (b + 15) & ~(size_t)15;
 }
 
-#define DZ_IMAX 4        // relaxation items (cell, row) per thread
 #define DZ_THREADS 512   // 16 warps, always (4 per SM sub-partition: 128 registers per thread)
