@@ -131,8 +131,15 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
 #pragma unroll
             for (int k = 0; k < KSREG; k++) a[k] = k < KS ? __ldg(Af + k * 32) : 0.0;
         }
+        // a row block shared by several warps is split by column block inside every group first (so that each group
+        // carries the same work on every SM sub-partition), then by group
+        const int bp = min(mp.nParts, NB), gp = max(1, mp.nParts / bp);
+        const int myB = mp.part % bp, myG = mp.part / bp;
+        const bool partOk = mp.part < bp * gp;
+        unsigned blkMask = 0;
+        for (int j = 0; j < NB; j++) if ((j % bp) == myB) blkMask |= 1u << j;
         for (int cg = CG - 1; cg >= 0; cg--) {
-            const bool mine = active && (cg % mp.nParts) == mp.part;
+            const bool mine = active && partOk && (cg % gp) == myG;
             double d[NB][2];
 #pragma unroll
             for (int j = 0; j < NB; j++) { d[j][0] = 0.0; d[j][1] = 0.0; }
@@ -145,7 +152,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                         if (k < KS) {
 #pragma unroll
                             for (int j = 0; j < NB; j++) {
-                                if (j < nbAct) {
+                                if (j < nbAct && ((blkMask >> j) & 1u)) {
                                     double b = xb[j * 8 * P + k * 4];
                                     dmma884(d[j][0], d[j][1], a[k], b);
                                 }
@@ -157,7 +164,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                         double av = __ldg(Af + k * 32);
 #pragma unroll
                         for (int j = 0; j < NB; j++) {
-                            if (j < nbAct) {
+                            if (j < nbAct && ((blkMask >> j) & 1u)) {
                                 double b = xb[j * 8 * P + k * 4];
                                 dmma884(d[j][0], d[j][1], av, b);
                             }
@@ -180,7 +187,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         const int col = cg * NB * 8 + j * 8 + qc * 2 + e;
-                        if (col < nCols) {
+                        if (col < nCols && ((blkMask >> j) & 1u)) {
                             const unsigned pos = colPos[col];
                             if (pos != 0xFFFFu) {
                                 double v = d[j][e];
@@ -248,12 +255,12 @@ __device__ __forceinline__ void dz_defer(const DeepzSched& sp, DevCallState* st,
 // stays zero and contributes nothing), they are only marked so that generator counts, statistics
 // and fetched zonotopes agree with the reference.  Marks the used generator columns of the
 // current layout that are identically zero.
-__device__ __forceinline__ void dz_mark_dead(DeepzSmem& S, unsigned* dead, const int* colOff, const double* X, int P,
-                                             int rows, int nCells, int tid, int NT) {
+__device__ __forceinline__ void dz_mark_dead(unsigned* dead, const int* colOff, const unsigned short* wUsed, const double* X,
+                                             int P, int rows, int nCells, int tid, int NT) {
     for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) dead[i] = 0;
     __syncthreads();
     for (int ci = tid >> 5; ci < nCells; ci += NT >> 5) {
-        const int cb = colOff[ci], w = S.wUsed[ci];
+        const int cb = colOff[ci], w = wUsed[ci];
         for (int j = 1 + (tid & 31); j < w; j += 32) {
             bool any = false;
             for (int r = 0; r < rows && !any; r++) any = X[(cb + j) * P + r] != 0.0;
@@ -356,7 +363,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             S.cellId[tid] = sp.pass == 0 ? idx : (sp.pass == 1 ? sp.retry_list[idx] : sp.big_list[idx]);
             if (STATS) S.cellNear[tid] = 0;
         }
-        for (int i = tid; i < nCells * CLR_MASK_WORDS; i += NT) (&S.mask[0][0])[i] = 0;
+        for (int i = tid; i < nCells * CLR_MASK_WORDS; i += NT) (&S.mask[0][0][0])[i] = 0;
         if (needDead) for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) { S.deadMask[0][i] = 0; S.deadMask[1][i] = 0; }
         __syncthreads();
 
@@ -399,10 +406,10 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             dz_layout(w[0], w[1], nCells, capCols, lane, off0, off1, keep, total);
             if (warp == 0) {
                 // with no pending generators the next layout equals the current one
-                if (lane < keep) { S.colOff[0][lane] = off0; S.colOff[1][lane] = off0; S.wUsed[lane] = (unsigned short)wu0; }
-                if (lane + 32 < keep) { S.colOff[0][lane + 32] = off1; S.colOff[1][lane + 32] = off1; S.wUsed[lane + 32] = (unsigned short)wu1; }
+                if (lane < keep) { S.colOff[0][lane] = off0; S.colOff[1][lane] = off0; S.wUsed[0][lane] = (unsigned short)wu0; S.uPend[0][lane] = 0; }
+                if (lane + 32 < keep) { S.colOff[0][lane + 32] = off1; S.colOff[1][lane + 32] = off1; S.wUsed[0][lane + 32] = (unsigned short)wu1; S.uPend[0][lane + 32] = 0; }
                 if (lane == 0) {
-                    S.colOff[0][keep] = total; S.colOff[1][keep] = total;
+                    S.colOff[0][keep] = total; S.colOff[1][keep] = total; S.nItems = 0;
                     if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
                     if (keep > 0) S.peakNeed = (float)(total + 8) / (float)keep;
                 }
@@ -418,7 +425,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             if (in.kind == 0) {
                 for (int it = tid; it < nCells * rows4; it += NT) {
                     const int ci = it / rows4, d = it - ci * rows4;
-                    const int cb = colOff[ci], p = S.wUsed[ci] - 1;
+                    const int cb = colOff[ci], p = S.wUsed[0][ci] - 1;
                     double c = 0.0, r = 0.0;
                     int rank = 0;
                     if (d < n) {
@@ -431,7 +438,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             } else {
                 for (int it = tid; it < nCells * rows4; it += NT) {
                     const int ci = it / rows4, d = it - ci * rows4;
-                    const int cb = colOff[ci], p = S.wUsed[ci] - 1;
+                    const int cb = colOff[ci], p = S.wUsed[0][ci] - 1;
                     const long long cell = S.cellId[ci];
                     const long long go = in.col_off[cell];
                     cur[cb * P + d] = d < n ? in.C[cell * n + d] : 0.0;
@@ -439,7 +446,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 }
             }
             for (int ci = warp; ci < nCells; ci += nWarps) {
-                const int cb = colOff[ci], w = S.wUsed[ci], wa = colOff[ci + 1] - cb;
+                const int cb = colOff[ci], w = S.wUsed[0][ci], wa = colOff[ci + 1] - cb;
                 for (int j = lane; j < wa; j += 32)
                     S.colPos[cb + j] = j < w ? (unsigned short)((cb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
             }
@@ -447,54 +454,64 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         }
 
         // ---- layers ------------------------------------------------------------------------------------------------
-        // invariant at the top: data in layout colOff[flip] (wUsed columns per cell), generators appended by the previous
-        // relaxation pending in mask / stage, next layout in colOff[flip ^ 1], colPos maps current -> next columns
+        // invariant at the top (parity `flip`): data in layout colOff[flip] with wUsed[flip] columns per cell, generators
+        // appended by the previous relaxation pending in mask[flip] / stage, next layout in colOff[flip ^ 1], colPos maps
+        // current -> next columns
         bool tileDead = false;
         for (int l = 0; l < L; l++) {
             const DevLayer& Ly = S.layers[l];
             const int* offNxt = S.colOff[flip ^ 1];
+            const unsigned short* wCur = S.wUsed[flip];
+            const unsigned (*pend)[CLR_MASK_WORDS] = S.mask[flip];
+            unsigned (*fresh)[CLR_MASK_WORDS] = S.mask[flip ^ 1];
             if (STATS && Ly.net_layer >= 0 && tid < nCells) {
                 // generators entering this layer, as the reference counts them
-                const int cb = S.colOff[flip][tid], w = S.wUsed[tid];
+                const int cb = S.colOff[flip][tid], w = wCur[tid];
                 int nz = 0;
                 for (int j = 1; j < w; j++) nz += !((S.deadMask[flipD][(cb + j) >> 5] >> ((cb + j) & 31)) & 1u);
-                for (int ww = 0; ww < CLR_MASK_WORDS; ww++) nz += __popc(S.mask[tid][ww]);
+                for (int ww = 0; ww < CLR_MASK_WORDS; ww++) nz += __popc(pend[tid][ww]);
                 S.cellPin[tid][Ly.net_layer] = (unsigned short)nz;
                 S.cellUnst[tid][Ly.net_layer] = 0;
             }
             const int act = Ly.act, collapse = Ly.collapse;
             const bool relax = !(act == CLR_ACT_ID && !collapse);
-            const int m = Ly.m, rowsP = clr_pad4(m);
+            const int m = Ly.m, rowsP = clr_pad4(m), mw = (m + 31) >> 5;
             dz_gemm<KSREG>(Ly, cur, oth, P, nCols, S.colPos, !relax, inplace, S.bar, phase, warp, lane, nWarps, a);
-            // weights of the next layer (or of the first layer for the next tile) while the relaxation runs
-            dz_load_a<KSREG>(S.layers[l + 1 < L ? l + 1 : 0], warp, lane, nWarps, a);
-            __syncthreads();   // all columns of the current layout consumed and moved
-            // pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i]
+            // Pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i].  In place this is safe
+            // without another barrier: the last mbarrier phase of the sweep means every warp has read every column.
             if (l > 0) {
-                for (int ci = warp; ci < nCells; ci += nWarps) {
-                    int col = offNxt[ci] + S.wUsed[ci];
-                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) {
-                        unsigned bits = S.mask[ci][ww];
-                        while (bits) {
-                            const int i = ww * 32 + __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            const double mu = stage[ci * stageW + i];
-                            const double* wc = Ly.Wcm + (size_t)i * m;
-                            for (int r = lane; r < rowsP; r += 32) {
-                                double v = r < m ? mu * __ldg(wc + r) : 0.0;
-                                oth[col * P + r] = v;
+                const int nIt = S.nItems;
+                if (nIt <= DZ_ITEMS_MAX) {
+                    for (int t = warp; t < nIt; t += nWarps) {
+                        const int i = S.itemRow[t], col = S.itemCol[t];
+                        const double mu = stage[S.itemCell[t] * stageW + i];
+                        const double* wc = Ly.Wcm + (size_t)i * m;
+                        for (int r = lane; r < rowsP; r += 32) oth[col * P + r] = r < m ? mu * __ldg(wc + r) : 0.0;
+                    }
+                } else {
+                    const int mwPrev = (S.layers[l - 1].m + 31) >> 5;
+                    int t = 0;
+                    for (int ci = 0; ci < nCells; ci++) {
+                        int col = offNxt[ci] + wCur[ci];
+                        for (int ww = 0; ww < mwPrev; ww++) {
+                            unsigned bits = pend[ci][ww];
+                            while (bits) {
+                                const int i = ww * 32 + __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                if ((t & (nWarps - 1)) == warp) {
+                                    const double mu = stage[ci * stageW + i];
+                                    const double* wc = Ly.Wcm + (size_t)i * m;
+                                    for (int r = lane; r < rowsP; r += 32) oth[col * P + r] = r < m ? mu * __ldg(wc + r) : 0.0;
+                                }
+                                t++; col++;
                             }
-                            col++;
                         }
                     }
                 }
-                __syncthreads();
-                if (tid < nCells) {
-                    int u = 0;
-                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) { u += __popc(S.mask[tid][ww]); S.mask[tid][ww] = 0; }
-                    S.wUsed[tid] = (unsigned short)(S.wUsed[tid] + u);
-                }
             }
+            for (int i = tid; i < nCells * CLR_MASK_WORDS; i += NT) (&fresh[0][0])[i] = 0;
+            // weights of the next layer (or of the first layer for the next tile) while the relaxation runs
+            dz_load_a<KSREG>(S.layers[l + 1 < L ? l + 1 : 0], warp, lane, nWarps, a);
             if (needDead) {
                 // dead marks follow their columns to the new positions
                 unsigned* dOld = S.deadMask[flipD];
@@ -507,11 +524,10 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 }
                 flipD ^= 1;
             }
-            { double* t = cur; cur = oth; oth = t; }
-            flip ^= 1;
-            __syncthreads();   // layout flipped: data in colOff[flip], wUsed updated, masks clear
-            const int* colOff = S.colOff[flip];
-            nCols = colOff[nCells];
+            { double* tp = cur; cur = oth; oth = tp; }
+            __syncthreads();   // [1] all columns moved to layout colOff[flip ^ 1]; pending generators materialised
+            const int* colOff = S.colOff[flip ^ 1];
+
             // ---- relaxation: bounds, lambda, mu, rows scaled in place; thread = (cell slot, row) ------------------------
             if (relax) {
                 const int G = NT / rowsP;                 // cell slots processed side by side
@@ -519,7 +535,8 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 if (slot < G && r < m) {
                     const double bias = __ldg(Ly.bias + r);
                     for (int ci = slot; ci < nCells; ci += G) {
-                        const int cb = colOff[ci], w = S.wUsed[ci];
+                        const int w = wCur[ci] + S.uPend[flip][ci];
+                        const int cb = colOff[ci];
                         double* y = cur + cb * P + r;
                         double c = y[0] + bias, lo, hi, rad = 0.0;
                         if (collapse) {
@@ -561,31 +578,31 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         else if (la != 1.0) { for (int j = 1; j < w; j++) y[j * P] = y[j * P] * la; }
                         if (unst) {
                             stage[ci * stageW + r] = mm;
-                            atomicOr(&S.mask[ci][r >> 5], 1u << (r & 31));
+                            atomicOr(&fresh[ci][r >> 5], 1u << (r & 31));
                         }
                     }
                 }
-                __syncthreads();
+                __syncthreads();   // [2]
             }
             // ---- next layout (every warp computes it; warp 0 publishes it) and the position table -----------------------
             {
                 int off0, off1, keep, total;
-                int w[2] = {0, 0}, wu[2] = {0, 0};
-                const int mw = (m + 31) >> 5;
+                int w[2] = {0, 0}, wu[2] = {0, 0}, uu[2] = {0, 0};
                 const int minW = (l + 1 < L && S.layers[l + 1].collapse) ? 2 : 1;   // a one-row map writes [c, r]
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int ci = lane + 32 * h;
                     if (ci < nCells) {
                         int u = 0;
-                        for (int ww = 0; ww < mw; ww++) u += __popc(S.mask[ci][ww]);
-                        wu[h] = collapse ? 2 : S.wUsed[ci];
+                        for (int ww = 0; ww < mw; ww++) u += __popc(fresh[ci][ww]);
+                        uu[h] = u;
+                        wu[h] = collapse ? 2 : wCur[ci] + S.uPend[flip][ci];
                         w[h] = max(max(colOff[ci + 1] - colOff[ci], wu[h] + u), minW);   // cells never shrink: they only move right
                         if (STATS && warp == 0 && Ly.net_layer >= 0) S.cellUnst[ci][Ly.net_layer] = (unsigned short)u;
                     }
                 }
                 dz_layout(w[0], w[1], nCells, capCols, lane, off0, off1, keep, total);
-                int* cn = S.colOff[flip ^ 1];
+                int* cn = S.colOff[flip];                // the layout the data just left is free: it becomes the next one
                 if (warp == 0) {
                     if (lane < keep) cn[lane] = off0;
                     if (lane + 32 < keep) cn[lane + 32] = off1;
@@ -593,6 +610,42 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         cn[keep] = total;
                         if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
                         if (keep > 0) S.peakNeed = fmaxf(S.peakNeed, (float)(total + 8) / (float)keep);
+                    }
+                } else if (warp == 1) {
+                    if (lane < keep) { S.wUsed[flip ^ 1][lane] = (unsigned short)wu[0]; S.uPend[flip ^ 1][lane] = (unsigned short)uu[0]; }
+                    if (lane + 32 < keep) { S.wUsed[flip ^ 1][lane + 32] = (unsigned short)wu[1]; S.uPend[flip ^ 1][lane + 32] = (unsigned short)uu[1]; }
+                }
+                // list of the generators just appended (cell, row, column in the layout after the next product)
+                int ub0 = lane < keep ? uu[0] : 0, ub1 = lane + 32 < keep ? uu[1] : 0;
+                {
+                    int s0 = ub0, s1 = ub1;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        int t0 = __shfl_up_sync(0xffffffffu, s0, dd);
+                        int t1 = __shfl_up_sync(0xffffffffu, s1, dd);
+                        if (lane >= dd) { s0 += t0; s1 += t1; }
+                    }
+                    const int tot0 = __shfl_sync(0xffffffffu, s0, 31);
+                    const int nIt = tot0 + __shfl_sync(0xffffffffu, s1, 31);
+                    ub0 = s0 - ub0; ub1 = tot0 + s1 - ub1;      // first item of cells lane, lane + 32
+                    if (tid == 0) S.nItems = nIt;
+                    if (nIt <= DZ_ITEMS_MAX) {
+                        for (int ci = warp; ci < keep; ci += nWarps) {
+                            const int nb = ci < 32 ? __shfl_sync(0xffffffffu, off0, ci & 31) : __shfl_sync(0xffffffffu, off1, ci & 31);
+                            const int wuse = ci < 32 ? __shfl_sync(0xffffffffu, wu[0], ci & 31) : __shfl_sync(0xffffffffu, wu[1], ci & 31);
+                            const int base = ci < 32 ? __shfl_sync(0xffffffffu, ub0, ci & 31) : __shfl_sync(0xffffffffu, ub1, ci & 31);
+                            int before = 0;
+                            for (int ww = 0; ww < mw; ww++) {
+                                const unsigned bits = fresh[ci][ww];
+                                if ((bits >> lane) & 1u) {
+                                    const int k = before + __popc(bits & ((1u << lane) - 1u));
+                                    S.itemCol[base + k] = (unsigned short)(nb + wuse + k);
+                                    S.itemCell[base + k] = (unsigned short)ci;
+                                    S.itemRow[base + k] = (unsigned short)(ww * 32 + lane);
+                                }
+                                before += __popc(bits);
+                            }
+                        }
                     }
                 }
                 // position table: cells dealt to the warps, lanes over a cell's columns
@@ -603,12 +656,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     for (int j = lane; j < wa; j += 32)
                         S.colPos[cb + j] = j < wuse ? (unsigned short)((nb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
                 }
-                if (collapse && warp == 1) {
-                    if (lane < keep) S.wUsed[lane] = 2;
-                    if (lane + 32 < keep) S.wUsed[lane + 32] = 2;
-                }
                 nCells = keep;
             }
+            flip ^= 1;
             if (nCells == 0) {
                 tileDead = true;
                 dz_load_a<KSREG>(S.layers[0], warp, lane, nWarps, a);   // the next tile starts at layer 0 again
@@ -616,9 +666,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 break;
             }
             nCols = colOff[nCells];          // columns of the current layout that the next product reads
-            __syncthreads();
+            __syncthreads();   // [3] next layout, position table and widths published
             if (needDead) {
-                if (Ly.remove_zero) dz_mark_dead(S, S.deadMask[flipD], colOff, cur, P, m, nCells, tid, NT);
+                if (Ly.remove_zero) dz_mark_dead(S.deadMask[flipD], colOff, S.wUsed[flip], cur, P, m, nCells, tid, NT);
                 else if (relax) { for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) S.deadMask[flipD][i] = 0; __syncthreads(); }
             }
         }
@@ -633,7 +683,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             int* rank0 = S.colOff[flip ^ 1];              // rank of a cell's first pending generator
             if (needDead) {
                 if (tid < nCells) {
-                    const int cb = colOff[tid], w = S.wUsed[tid];
+                    const int cb = colOff[tid], w = S.wUsed[flip][tid];
                     int k = 0;
                     colRank[cb] = 0xFFFF;
                     for (int j = 1; j < w; j++) {
@@ -641,7 +691,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         colRank[cb + j] = dd ? (unsigned short)0xFFFF : (unsigned short)(k++);
                     }
                     int u = 0;
-                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[tid][ww]);
+                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[flip][tid][ww]);
                     rank0[tid] = k;
                     if (STATS) atomicMax(&S.sMaxP, k + u);
                     if (out.keep_cap > 0) {
@@ -653,9 +703,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
             for (int it = tid; it < nCells * mOut; it += NT) {
                 const int ci = it / mOut, r = it - ci * mOut;
-                const int cb = colOff[ci], w = S.wUsed[ci];
+                const int cb = colOff[ci], w = S.wUsed[flip][ci];
                 const double* y = cur + cb * P + r;
-                const unsigned mwv = S.mask[ci][r >> 5];
+                const unsigned mwv = S.mask[flip][ci][r >> 5];
                 const bool pend = (mwv >> (r & 31)) & 1u;     // this row's own appended generator mu * e_r
                 const double mu = pend ? stage[ci * stageW + r] : 0.0;
                 double c = y[0], lo, hi;
@@ -683,9 +733,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         if (k != 0xFFFF && k < out.keep_cap) g[(size_t)k * mOut] = y[j * P];
                     }
                     int k0 = rank0[ci], u = 0;
-                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[ci][ww]);
+                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[flip][ci][ww]);
                     int rank = __popc(mwv & ((1u << (r & 31)) - 1u));
-                    for (int ww = 0; ww < (r >> 5); ww++) rank += __popc(S.mask[ci][ww]);
+                    for (int ww = 0; ww < (r >> 5); ww++) rank += __popc(S.mask[flip][ci][ww]);
                     for (int k = 0; k < u; k++)
                         if (k0 + k < out.keep_cap) g[(size_t)(k0 + k) * mOut] = (pend && k == rank) ? mu : 0.0;
                 }

@@ -39,6 +39,8 @@ struct DeepzSched {
     double* workspace;        // pass 2: gridDim.x * cap doubles
 };
 
+#define DZ_ITEMS_MAX 384   // pending generators listed per tile (more: the slow walk over the masks)
+
 struct DeepzSmem {
     unsigned long long bar[2];                // mbarriers of the in-place layer product (one phase per column group)
     int nCells, tileT, more;
@@ -46,9 +48,12 @@ struct DeepzSmem {
     long long firstIdx;
     float peakNeed;
     int colOff[2][CLR_TILE_CELLS_MAX + 1];    // cell offsets of the current and of the next layout
-    unsigned short wUsed[CLR_TILE_CELLS_MAX]; // columns of a cell that hold data (centre + generators)
+    unsigned short wUsed[2][CLR_TILE_CELLS_MAX];   // columns of a cell that hold data (centre + generators), per layout
+    unsigned short uPend[2][CLR_TILE_CELLS_MAX];   // generators of a cell still pending (appended by the last relaxation)
+    int nItems;                                    // pending generators of the tile listed in item*
+    unsigned short itemCol[DZ_ITEMS_MAX], itemCell[DZ_ITEMS_MAX], itemRow[DZ_ITEMS_MAX];
     long long cellId[CLR_TILE_CELLS_MAX];
-    unsigned mask[CLR_TILE_CELLS_MAX][CLR_MASK_WORDS];   // rows whose relaxation appended a generator (pending: mu in the staging area)
+    unsigned mask[2][CLR_TILE_CELLS_MAX][CLR_MASK_WORDS];   // rows whose relaxation appended a generator: [pending | being written]
     unsigned short colPos[CLR_NCOL_MAX];      // column of the current layout -> column of the next one (0x8000: centre, 0xFFFF: unused)
     unsigned deadMask[2][CLR_NCOL_MAX / 32];  // generators the reference's remove_zero_columns has dropped
     double hlo[CLR_HULL_MAX], hhi[CLR_HULL_MAX];
