@@ -35,6 +35,7 @@ struct Compiled {            // one (network, pre/post-processing) pair on the d
     int ksreg = 8;
     int warps = 8;
     int stored_width = 0;
+    int point_code = 1;
     int inplace = 1;
     int worst_cols_growth = 0;
 };
@@ -284,6 +285,53 @@ int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Com
     P.total_doubles = (int)image.size();
     if ((rc = upload(ctx, c, image, &P.image))) { free_compiled(c); return rc; }
     c->stored_width = ro_stored_width(P.dims, P.L);
+    P.small_ni = P.small_no = P.stotal = 0;
+    P.simage = nullptr;
+    c->point_code = c->stored_width <= 128 ? 1 : 2;
+    if (c->stored_width <= 8) {
+        // packed image for narrow networks (ro_mlp_small): widths of the materialised vectors
+        int win = n_in, wout = 0;
+        for (int l = 0; l < P.L;) {
+            if (l + 1 < P.L) { wout = std::max(wout, P.dims[l + 2]); win = std::max(win, P.dims[l + 2]); l += 2; }
+            else { wout = std::max(wout, P.dims[l + 1]); win = std::max(win, P.dims[l + 1]); l += 1; }
+        }
+        const int NI = win <= 4 ? 4 : 8;
+        const int NO = (NI == 4 && wout <= 2) ? 2 : 8;
+        P.small_ni = NI; P.small_no = NO;
+        c->point_code = NI * 16 + NO;
+        std::vector<double> simg;
+        for (int l = 0; l < P.L;) {
+            const HostLayer& h1 = layers[l];
+            if (l + 1 < P.L) {
+                const HostLayer& h2 = layers[l + 1];
+                const int ST = NI + NO + 2;
+                P.soff[l] = (int)simg.size();
+                simg.resize(simg.size() + (size_t)h1.m * ST, 0.0);
+                double* rec = simg.data() + P.soff[l];
+                for (int i = 0; i < h1.m; i++) {
+                    for (int k = 0; k < h1.n; k++) rec[i * ST + k] = h1.W[(size_t)k * h1.m + i];
+                    for (int o = 0; o < h2.m; o++) rec[i * ST + NI + o] = h2.W[(size_t)i * h2.m + o];
+                    rec[i * ST + NI + NO] = h1.b[i];
+                }
+                P.soff[l + 1] = (int)simg.size();
+                simg.resize(simg.size() + NO + (NO & 1), 0.0);
+                for (int o = 0; o < h2.m; o++) simg[P.soff[l + 1] + o] = h2.b[o];
+                l += 2;
+            } else {
+                const int ST1 = NI + 2;
+                P.soff[l] = (int)simg.size();
+                simg.resize(simg.size() + (size_t)h1.m * ST1, 0.0);
+                double* rec = simg.data() + P.soff[l];
+                for (int i = 0; i < h1.m; i++) {
+                    for (int k = 0; k < h1.n; k++) rec[i * ST1 + k] = h1.W[(size_t)k * h1.m + i];
+                    rec[i * ST1 + NI] = h1.b[i];
+                }
+                l += 1;
+            }
+        }
+        P.stotal = (int)simg.size();
+        if ((rc = upload(ctx, c, simg, &P.simage))) { free_compiled(c); return rc; }
+    }
     const int ks_opts[4] = {8, 16, 25, 32};
     c->ksreg = 32;
     for (int o = 0; o < 4; o++) if (maxKsReg <= ks_opts[o]) { c->ksreg = ks_opts[o]; break; }
@@ -741,12 +789,12 @@ int32_t clr_deepz_fetch_zonotopes(clr_ctx* ctx, int32_t* out_ncols, double* out_
 }  // extern "C"
 
 namespace {
-template <int MAXW>
+template <int CODE>
 int launch_points(clr_ctx* ctx, const PointNet& P, int nx, int64_t N, const double* X, double* U) {
-    size_t wbytes = sizeof(double) * (size_t)P.total_doubles;
+    size_t wbytes = sizeof(double) * (size_t)(CODE > 2 ? P.stotal : P.total_doubles);
     int in_smem = wbytes <= (size_t)ctx->smem_optin - 1024;
     size_t smem = in_smem ? wbytes : 0;
-    auto kern = forward_points_kernel<MAXW>;
+    auto kern = forward_points_kernel<CODE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = in_smem ? std::max(1, std::min(8, (int)((size_t)ctx->smem_optin / (smem + 1024)))) : 8;
     int grid = (int)std::min<int64_t>((N + 127) / 128, (int64_t)ctx->sms * per_sm);
@@ -756,14 +804,24 @@ int launch_points(clr_ctx* ctx, const PointNet& P, int nx, int64_t N, const doub
     return 0;
 }
 
-template <int PLANT, int MAXW>
+int launch_points_code(clr_ctx* ctx, int code, const PointNet& P, int nx, int64_t N, const double* X, double* U) {
+    switch (code) {
+        case 66: return launch_points<66>(ctx, P, nx, N, X, U);
+        case 72: return launch_points<72>(ctx, P, nx, N, X, U);
+        case 136: return launch_points<136>(ctx, P, nx, N, X, U);
+        case 1: return launch_points<1>(ctx, P, nx, N, X, U);
+        default: return launch_points<2>(ctx, P, nx, N, X, U);
+    }
+}
+
+template <int PLANT, int CODE>
 int launch_rollout_t(clr_ctx* ctx, const PointNet& P, const RolloutArgs& A) {
-    size_t wbytes = sizeof(double) * (size_t)P.total_doubles;
+    size_t wbytes = sizeof(double) * (size_t)(CODE > 2 ? P.stotal : P.total_doubles);
     int in_smem = wbytes <= (size_t)ctx->smem_optin - 1024;
     size_t smem = in_smem ? wbytes : 0;
-    auto kern = rollout_kernel<PLANT, MAXW>;
+    auto kern = rollout_kernel<PLANT, CODE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = in_smem ? std::max(1, std::min(8, (int)((size_t)ctx->smem_optin / (smem + 1024)))) : 8;
+    int per_sm = in_smem ? std::max(1, std::min(4, (int)((size_t)ctx->smem_optin / (smem + 1024)))) : 4;
     int grid = (int)std::min<int64_t>((A.N + 127) / 128, (int64_t)ctx->sms * per_sm);
     kern<<<grid, 128, smem, ctx->stream>>>(P, A, in_smem);
     CU(cudaGetLastError());
@@ -771,11 +829,33 @@ int launch_rollout_t(clr_ctx* ctx, const PointNet& P, const RolloutArgs& A) {
     return 0;
 }
 
+// narrow networks whose packed image fits beside the state slots: RO_R trajectories per thread
+template <int PLANT, int CODE>
+int launch_rollout_blocked(clr_ctx* ctx, const PointNet& P, const RolloutArgs& A) {
+    constexpr int NS = PlantDims<PLANT>::NS, NC = PlantDims<PLANT>::NC;
+    const size_t slots = sizeof(double) * RO_R * (NS + NC) * 128;
+    const size_t wbytes = sizeof(double) * (size_t)P.stotal;
+    if (slots + wbytes > (size_t)ctx->smem_optin / 4 - 1024) return launch_rollout_t<PLANT, CODE>(ctx, P, A);
+    const size_t smem = slots + wbytes;
+    auto kern = rollout_blocked_kernel<PLANT, CODE>;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t span = 128 * RO_R;
+    int grid = (int)std::min<int64_t>((A.N + span - 1) / span, (int64_t)ctx->sms * 4);
+    kern<<<grid, 128, smem, ctx->stream>>>(P, A, 1);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 template <int PLANT>
-int launch_rollout_p(clr_ctx* ctx, int stored, const PointNet& P, const RolloutArgs& A) {
-    if (stored <= 8) return launch_rollout_t<PLANT, 8>(ctx, P, A);
-    if (stored <= 128) return launch_rollout_t<PLANT, 128>(ctx, P, A);
-    return launch_rollout_t<PLANT, 512>(ctx, P, A);
+int launch_rollout_p(clr_ctx* ctx, int code, const PointNet& P, const RolloutArgs& A) {
+    switch (code) {
+        case 66: return launch_rollout_blocked<PLANT, 66>(ctx, P, A);
+        case 72: return launch_rollout_blocked<PLANT, 72>(ctx, P, A);
+        case 136: return launch_rollout_blocked<PLANT, 136>(ctx, P, A);
+        case 1: return launch_rollout_t<PLANT, 1>(ctx, P, A);
+        default: return launch_rollout_t<PLANT, 2>(ctx, P, A);
+    }
 }
 }  // namespace
 
@@ -801,9 +881,7 @@ int32_t clr_forward_points(clr_ctx* ctx, const clr_net* net_c, const clr_prepost
         if ((rc = ensure(ctx, &ctx->d_io[4], &ctx->io_bytes[4], sizeof(double) * (size_t)m * N))) return rc;
         dU = (double*)ctx->d_io[4];
     }
-    if (c->stored_width <= 8) rc = launch_points<8>(ctx, c->pnet, nx, N, (const double*)dX, dU);
-    else if (c->stored_width <= 128) rc = launch_points<128>(ctx, c->pnet, nx, N, (const double*)dX, dU);
-    else rc = launch_points<512>(ctx, c->pnet, nx, N, (const double*)dX, dU);
+    rc = launch_points_code(ctx, c->point_code, c->pnet, nx, N, (const double*)dX, dU);
     if (rc) return rc;
     if (!dev_io) {
         CU(cudaMemcpyAsync(U, dU, sizeof(double) * (size_t)m * N, cudaMemcpyDeviceToHost, ctx->stream));
@@ -875,10 +953,10 @@ int32_t clr_rollout(clr_ctx* ctx, const clr_net* net_c, const clr_prepost* pp, i
         if (log_cap > 0) { A.log_n = (int*)(base + oLn); A.log_t = (double*)(base + oLt); A.log_u = (double*)(base + oLu); }
     }
     switch (plant) {
-        case CLR_PLANT_UNICYCLE: rc = launch_rollout_p<CLR_PLANT_UNICYCLE>(ctx, c->stored_width, c->pnet, A); break;
-        case CLR_PLANT_TORA: rc = launch_rollout_p<CLR_PLANT_TORA>(ctx, c->stored_width, c->pnet, A); break;
-        case CLR_PLANT_ACC: rc = launch_rollout_p<CLR_PLANT_ACC>(ctx, c->stored_width, c->pnet, A); break;
-        default: rc = launch_rollout_p<CLR_PLANT_INVPEND>(ctx, c->stored_width, c->pnet, A); break;
+        case CLR_PLANT_UNICYCLE: rc = launch_rollout_p<CLR_PLANT_UNICYCLE>(ctx, c->point_code, c->pnet, A); break;
+        case CLR_PLANT_TORA: rc = launch_rollout_p<CLR_PLANT_TORA>(ctx, c->point_code, c->pnet, A); break;
+        case CLR_PLANT_ACC: rc = launch_rollout_p<CLR_PLANT_ACC>(ctx, c->point_code, c->pnet, A); break;
+        default: rc = launch_rollout_p<CLR_PLANT_INVPEND>(ctx, c->point_code, c->pnet, A); break;
     }
     if (rc) return rc;
     if (!dev_io) {

@@ -25,6 +25,10 @@ struct PointNet {
     const double* b[RO_MAX_LAYERS];
     int off_rm[RO_MAX_LAYERS], off_cm[RO_MAX_LAYERS], off_b[RO_MAX_LAYERS];   // offsets in the smem image
     const double* image;          // device: all weights in smem-image order
+    // packed image of narrow networks (every materialised vector has at most 8 entries), see ro_mlp_small
+    int small_ni, small_no, stotal;
+    int soff[RO_MAX_LAYERS];
+    const double* simage;
 };
 
 __device__ __forceinline__ double ro_act(int act, double s) {
@@ -66,6 +70,7 @@ __device__ __forceinline__ void ro_mlp(const PointNet& net, const double* __rest
             } else {
                 for (int o = 0; o < m2; o++) vb[o] = 0.0;
             }
+#pragma unroll 4
             for (int i = 0; i < m; i++) {
                 double s = 0.0;
                 if (MAXW <= 8) {
@@ -125,6 +130,89 @@ __device__ __forceinline__ void ro_mlp(const PointNet& net, const double* __rest
     }
 }
 
+// Narrow networks (e.g. Unicycle 4 -> 500 -> 2): every materialised vector fits NI / NO registers.  The host packs, per
+// hidden neuron i of a layer pair, one zero-padded record [W1[i, 0..NI) | W2[0..NO, i] | b1[i] | 0], so the inner loop is
+// NI/2 + NO/2 + 1 broadcast shared loads (128-bit) and NI + NO + 2 FP64 instructions, no predicates.
+template <int NI, int NO>
+__device__ __forceinline__ void ro_mlp_small(const PointNet& net, const double* __restrict__ w, const double* xin,
+                                             double* uout) {
+    constexpr int NV = NI > NO ? NI : NO;
+    double va[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) va[k] = k < net.n_in ? xin[k] : 0.0;
+    int l = 0;
+    while (l < net.L) {
+        const int m = net.dims[l + 1];
+        if (l + 1 < net.L) {
+            constexpr int ST = NI + NO + 2;
+            const double* rec = w + net.soff[l];
+            const double* b2 = w + net.soff[l + 1];
+            const int a1 = net.act[l], a2 = net.act[l + 1];
+            double vb[NO];
+#pragma unroll
+            for (int o = 0; o < NO; o++) vb[o] = 0.0;
+            if (a1 == CLR_ACT_RELU) {
+#pragma unroll 4
+                for (int i = 0; i < m; i++) {
+                    const double2* r2 = reinterpret_cast<const double2*>(rec + i * ST);
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NI / 2; k++) { const double2 wv = r2[k]; s = fma(wv.x, va[2 * k], s); s = fma(wv.y, va[2 * k + 1], s); }
+                    s += rec[i * ST + NI + NO];
+                    const double h = fmax(s, 0.0);
+#pragma unroll
+                    for (int o = 0; o < NO / 2; o++) { const double2 vv = r2[NI / 2 + o]; vb[2 * o] = fma(vv.x, h, vb[2 * o]); vb[2 * o + 1] = fma(vv.y, h, vb[2 * o + 1]); }
+                }
+            } else {
+                for (int i = 0; i < m; i++) {
+                    const double2* r2 = reinterpret_cast<const double2*>(rec + i * ST);
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NI / 2; k++) { const double2 wv = r2[k]; s = fma(wv.x, va[2 * k], s); s = fma(wv.y, va[2 * k + 1], s); }
+                    s += rec[i * ST + NI + NO];
+                    const double h = ro_act(a1, s);
+#pragma unroll
+                    for (int o = 0; o < NO / 2; o++) { const double2 vv = r2[NI / 2 + o]; vb[2 * o] = fma(vv.x, h, vb[2 * o]); vb[2 * o + 1] = fma(vv.y, h, vb[2 * o + 1]); }
+                }
+            }
+            const int m2 = net.dims[l + 2];
+#pragma unroll
+            for (int o = 0; o < NV; o++) va[o] = (o < NO && o < m2) ? ro_act(a2, vb[o < NO ? o : 0] + b2[o < NO ? o : 0]) : 0.0;
+            l += 2;
+        } else {
+            constexpr int ST1 = NI + 2;
+            const double* rec = w + net.soff[l];
+            const int a1 = net.act[l];
+            double vb[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                vb[i] = 0.0;
+                if (i < m) {
+                    const double2* r2 = reinterpret_cast<const double2*>(rec + i * ST1);
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NI / 2; k++) { const double2 wv = r2[k]; s = fma(wv.x, va[2 * k], s); s = fma(wv.y, va[2 * k + 1], s); }
+                    vb[i] = ro_act(a1, s + rec[i * ST1 + NI]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NV; i++) va[i] = vb[i];
+            l += 1;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++) if (k < net.m_out) uout[k] = va[k];
+}
+
+// CODE selects the evaluator: NI * 16 + NO for narrow networks (66: 4/2, 72: 4/8, 136: 8/8), 1 / 2: generic with 128 / 512
+// materialised entries.  xin / uout hold at least 8 entries for the narrow codes.
+template <int CODE>
+__device__ __forceinline__ void ro_eval(const PointNet& net, const double* __restrict__ w, const double* xin, double* uout) {
+    if (CODE == 1) ro_mlp<128>(net, w, xin, uout);
+    else if (CODE == 2) ro_mlp<512>(net, w, xin, uout);
+    else ro_mlp_small<(CODE >> 4), (CODE & 15)>(net, w, xin, uout);
+}
+
 // widths that must be materialised by ro_mlp (host uses the same rule to pick MAXW)
 __host__ __device__ inline int ro_stored_width(const int* dims, int L) {
     int w = dims[0], l = 0;
@@ -135,21 +223,33 @@ __host__ __device__ inline int ro_stored_width(const int* dims, int L) {
     return w;
 }
 
-__device__ __forceinline__ const double* ro_stage_weights(const PointNet& net, double* sm, bool in_smem) {
-    if (!in_smem) return net.image;
-    for (int i = threadIdx.x; i < net.total_doubles; i += blockDim.x) sm[i] = __ldg(net.image + i);
+__device__ __forceinline__ const double* ro_stage_weights(const PointNet& net, double* sm, bool in_smem, bool narrow) {
+    const double* img = narrow ? net.simage : net.image;
+    const int cnt = narrow ? net.stotal : net.total_doubles;
+    if (!in_smem) return img;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) sm[i] = __ldg(img + i);
     __syncthreads();
     return sm;
 }
 
-template <int MAXW>
+template <int CODE>
 __global__ void __launch_bounds__(128)
 forward_points_kernel(PointNet net, int nx, long long N, const double* __restrict__ X, double* __restrict__ U,
                       int in_smem) {
     extern __shared__ __align__(16) double ro_sm[];
-    const double* w = ro_stage_weights(net, ro_sm, in_smem != 0);
-    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < N; j += (long long)gridDim.x * blockDim.x)
-        ro_mlp<MAXW>(net, w, X + j * nx, U + j * net.m_out);
+    const double* w = ro_stage_weights(net, ro_sm, in_smem != 0, CODE > 2);
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < N; j += (long long)gridDim.x * blockDim.x) {
+        if (CODE > 2) {
+            double x[8], u[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) x[k] = k < nx ? X[j * nx + k] : 0.0;
+            ro_eval<CODE>(net, w, x, u);
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < net.m_out) U[j * net.m_out + k] = u[k];
+        } else {
+            ro_eval<CODE>(net, w, X + j * nx, U + j * net.m_out);
+        }
+    }
 }
 
 // ---- plants on the extended state [x; w; u]; only the n_state leading entries have dynamics ---------
@@ -163,8 +263,10 @@ template <> struct PlantDims<CLR_PLANT_INVPEND> { static constexpr int NS = 2, N
 template <int PLANT>
 __device__ __forceinline__ void plant_rhs(const double* x, const double* q, double* dx) {
     if (PLANT == CLR_PLANT_UNICYCLE) {            // models/Unicycle/Unicycle.jl:36-47
-        dx[0] = x[3] * cos(x[2]);
-        dx[1] = x[3] * sin(x[2]);
+        double sn, cs;
+        sincos(x[2], &sn, &cs);
+        dx[0] = x[3] * cs;
+        dx[1] = x[3] * sn;
         dx[2] = q[2];
         dx[3] = q[1] + q[0];
     } else if (PLANT == CLR_PLANT_TORA) {         // models/TORA/TORA.jl:46-55
@@ -426,12 +528,12 @@ __device__ __forceinline__ void ro_rk4(double* x, const double* q, double t0, do
     }
 }
 
-template <int PLANT, int MAXW>
-__global__ void __launch_bounds__(128)
+template <int PLANT, int CODE>
+__global__ void __launch_bounds__(128, 4)
 rollout_kernel(PointNet net, RolloutArgs A, int in_smem) {
     constexpr int NS = PlantDims<PLANT>::NS, ND = PlantDims<PLANT>::ND, NC = PlantDims<PLANT>::NC;
     extern __shared__ __align__(16) double ro_sm[];
-    const double* w = ro_stage_weights(net, ro_sm, in_smem != 0);
+    const double* w = ro_stage_weights(net, ro_sm, in_smem != 0, CODE > 2);
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < A.N; j += (long long)gridDim.x * blockDim.x) {
         double x[NS], q[ND + NC];
 #pragma unroll
@@ -441,7 +543,7 @@ rollout_kernel(PointNet net, RolloutArgs A, int in_smem) {
             double xin[8], u[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) xin[i] = i < NS ? x[i] : 0.0;
-            ro_mlp<MAXW>(net, w, xin, u);
+            ro_eval<CODE>(net, w, xin, u);
             const long long cell = (long long)it * A.N + j;
 #pragma unroll
             for (int i = 0; i < NC; i++) A.U[cell * NC + i] = u[i];
@@ -457,6 +559,145 @@ rollout_kernel(PointNet net, RolloutArgs A, int in_smem) {
             if (A.nreject) A.nreject[cell] = nrej;
 #pragma unroll
             for (int i = 0; i < NS; i++) A.X_end[cell * NS + i] = x[i];
+            t = t1;
+        }
+    }
+}
+
+// Register-blocked evaluation of a narrow two-stage network for R points at once: every weight record is
+// loaded from shared memory once and used for R trajectories, which takes the shared-memory pipe (the limiter
+// of the one-point version: 4 broadcast loads per neuron) off the critical path.  Same arithmetic per point
+// as ro_mlp_small.
+template <int NI, int NO, int R>
+__device__ __forceinline__ void ro_mlp_small_blocked(const PointNet& net, const double* __restrict__ w, double (&va)[R][8],
+                                                     double (&uo)[R][8]) {
+    int l = 0;
+    while (l < net.L) {
+        const int m = net.dims[l + 1];
+        if (l + 1 < net.L) {
+            constexpr int ST = NI + NO + 2;
+            const double* rec = w + net.soff[l];
+            const double* b2 = w + net.soff[l + 1];
+            const int a1 = net.act[l], a2 = net.act[l + 1];
+            const int m2 = net.dims[l + 2];
+            double vb[R][NO];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int o = 0; o < NO; o++) vb[r][o] = 0.0;
+            const bool relu = a1 == CLR_ACT_RELU;
+#pragma unroll 2
+            for (int i = 0; i < m; i++) {
+                const double2* r2 = reinterpret_cast<const double2*>(rec + i * ST);
+                double2 wv[NI / 2], vv[NO / 2];
+#pragma unroll
+                for (int k = 0; k < NI / 2; k++) wv[k] = r2[k];
+#pragma unroll
+                for (int o = 0; o < NO / 2; o++) vv[o] = r2[NI / 2 + o];
+                const double b1 = rec[i * ST + NI + NO];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NI / 2; k++) { s = fma(wv[k].x, va[r][2 * k], s); s = fma(wv[k].y, va[r][2 * k + 1], s); }
+                    s += b1;
+                    const double h = relu ? fmax(s, 0.0) : ro_act(a1, s);
+#pragma unroll
+                    for (int o = 0; o < NO / 2; o++) { vb[r][2 * o] = fma(vv[o].x, h, vb[r][2 * o]); vb[r][2 * o + 1] = fma(vv[o].y, h, vb[r][2 * o + 1]); }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int o = 0; o < 8; o++) va[r][o] = (o < NO && o < m2) ? ro_act(a2, vb[r][o < NO ? o : 0] + b2[o < NO ? o : 0]) : 0.0;
+            l += 2;
+        } else {
+            constexpr int ST1 = NI + 2;
+            const double* rec = w + net.soff[l];
+            const int a1 = net.act[l];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                double vb[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    vb[i] = 0.0;
+                    if (i < m) {
+                        const double2* r2 = reinterpret_cast<const double2*>(rec + i * ST1);
+                        double s = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NI / 2; k++) { const double2 wv = r2[k]; s = fma(wv.x, va[r][2 * k], s); s = fma(wv.y, va[r][2 * k + 1], s); }
+                        vb[i] = ro_act(a1, s + rec[i * ST1 + NI]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) va[r][i] = vb[i];
+            }
+            l += 1;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) uo[r][k] = va[r][k];
+}
+
+// Narrow-network rollouts: a thread owns RO_R trajectories.  Per period the controller is evaluated for all of
+// them at once (register blocked), then each one is integrated in turn; states and controls live in
+// thread-private shared-memory slots in between, so the ODE code exists once.
+#define RO_R 4
+template <int PLANT, int CODE>
+__global__ void __launch_bounds__(128, 4)
+rollout_blocked_kernel(PointNet net, RolloutArgs A, int in_smem) {
+    constexpr int NS = PlantDims<PLANT>::NS, ND = PlantDims<PLANT>::ND, NC = PlantDims<PLANT>::NC;
+    constexpr int NI = CODE >> 4, NO = CODE & 15;
+    extern __shared__ __align__(16) double ro_sm[];
+    const int tid = threadIdx.x;
+    double* xs = ro_sm;                                   // [RO_R][NS][128]
+    double* us = xs + RO_R * NS * 128;                    // [RO_R][NC][128]
+    double* wsm = us + RO_R * NC * 128;
+    const double* w = ro_stage_weights(net, wsm, in_smem != 0, true);
+    const long long span = 128ll * RO_R;
+    for (long long base = blockIdx.x * span; base < A.N; base += (long long)gridDim.x * span) {
+#pragma unroll
+        for (int r = 0; r < RO_R; r++) {
+            const long long j = base + r * 128 + tid;
+#pragma unroll
+            for (int i = 0; i < NS; i++) xs[(r * NS + i) * 128 + tid] = j < A.N ? A.x0[j * NS + i] : 0.0;
+        }
+        double t = A.t0;
+        for (int it = 0; it < A.iters; it++) {
+            {
+                double va[RO_R][8], uo[RO_R][8];
+#pragma unroll
+                for (int r = 0; r < RO_R; r++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++) va[r][i] = i < NS ? xs[(r * NS + (i < NS ? i : 0)) * 128 + tid] : 0.0;
+                ro_mlp_small_blocked<NI, NO, RO_R>(net, w, va, uo);
+#pragma unroll
+                for (int r = 0; r < RO_R; r++)
+#pragma unroll
+                    for (int i = 0; i < NC; i++) us[(r * NC + i) * 128 + tid] = uo[r][i];
+            }
+            const double t1 = it < A.iters - 1 ? t + A.tau : A.T;
+            for (int r = 0; r < RO_R; r++) {
+                const long long j = base + r * 128 + tid;
+                if (j >= A.N) continue;
+                double x[NS], q[ND + NC];
+#pragma unroll
+                for (int i = 0; i < NS; i++) x[i] = xs[(r * NS + i) * 128 + tid];
+                const long long cell = (long long)it * A.N + j;
+#pragma unroll
+                for (int i = 0; i < NC; i++) { q[ND + i] = us[(r * NC + i) * 128 + tid]; A.U[cell * NC + i] = q[ND + i]; }
+#pragma unroll
+                for (int i = 0; i < ND; i++) q[i] = A.Wd[cell * ND + i];
+                int nacc = 0, nrej = 0;
+                if (A.alg == CLR_ALG_TSIT5) ro_tsit5<PLANT>(x, q, t, t1, A, cell, nacc, nrej);
+                else { ro_rk4<PLANT>(x, q, t, t1, A.substeps); nacc = A.substeps; }
+                if (A.naccept) A.naccept[cell] = nacc;
+                if (A.nreject) A.nreject[cell] = nrej;
+#pragma unroll
+                for (int i = 0; i < NS; i++) { A.X_end[cell * NS + i] = x[i]; xs[(r * NS + i) * 128 + tid] = x[i]; }
+            }
             t = t1;
         }
     }
