@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+DFMA_PEAK_TFLOPS = 36.2   # measured FP64 FMA issue peak, same file (the rollout kernel is FP64-issue bound, not HBM bound)
 DMMA_PEAK_TFLOPS = 37.0   # measured on this pool's B200: profiles/microbench/r01_dmma_bench_b200.txt (mma.sync f64)
 METRIC = "zonotope controller propagations/sec (cells x steps)"
 
@@ -319,9 +320,12 @@ def run_ours(args):
                 c.record(stream)
             ctx.synchronize()
             ms = parallel.max_over_ranks(a.elapsed_time(c) / reps, device=dev)
-            byts = 88.0 * N * iters
+            byts = 88.0 * N * iters                      # 88 B per trajectory-period
+            flops = 6000.0 * N * iters                   # controller: 2 * (500*4 + 2*500) per trajectory-period
             res[alg] = {"value": world * N / (ms * 1e-3), "unit": "trajectories/s", "ms": ms,
-                        "hbm_GBps_algorithmic": byts / (ms * 1e-3) / 1e9}
+                        "hbm_GBps_algorithmic": byts / (ms * 1e-3) / 1e9,
+                        "controller_fp64_TFLOPs": flops / (ms * 1e-3) / 1e12,
+                        "frac_of_fp64_fma_peak": flops / (ms * 1e-3) / 1e12 / DFMA_PEAK_TFLOPS}
         line["secondary"] = {"metric": "sim trajectories/sec", "config": f"Unicycle, {N} trajectories per GPU x {iters} "
                              "control periods, 4->500->2 ReLU controller; Tsit5 = the reference's solver, RK4 = 4 fixed steps / period",
                              **res}

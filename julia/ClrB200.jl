@@ -1,0 +1,130 @@
+# ClrB200.jl -- the reference-side binding of libclr_b200.so (see INTEGRATION.md).
+#
+# NOT EXECUTED IN THIS REPOSITORY: the build image has no Julia.  It is the shim a maintainer of
+# ClosedLoopReachability.jl would add; every `ccall` below mirrors one prototype of include/clr_b200.h and the
+# Python ctypes mirror (closedloopreachability.jl_b200/_lib.py, runtime.py) exercises exactly the same call
+# sequences in the tests.
+module ClrB200
+
+using LazySets: LazySets, Hyperrectangle, Zonotope, Interval, center, genmat, ngens, low, high,
+                box_approximation, radius_hyperrectangle, dim
+using ControllerFormats: FeedforwardNetwork, DenseLayerOp, Id, ReLU, Sigmoid, Tanh
+
+const LIB = get(ENV, "CLR_B200_LIB", "libclr_b200.so")
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:clr_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, out)
+        rc == 0 || error(unsafe_string(ccall((:clr_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        ctx = new(out[])
+        finalizer(c -> ccall((:clr_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.h), ctx)
+        return ctx
+    end
+end
+
+function check(ctx::Context, rc::Int32)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:clr_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h))
+    # CLR_ERR_ARG (-1) / CLR_ERR_DIM (-3) are what src/solve.jl:88-99, :130-134 raise as ArgumentError
+    (rc == -1 || rc == -3) ? throw(ArgumentError(msg)) : error("libclr_b200 ($rc): $msg")
+end
+
+act_id(::Id) = Int32(0); act_id(::ReLU) = Int32(1); act_id(::Sigmoid) = Int32(2); act_id(::Tanh) = Int32(3)
+
+struct DeviceNetwork
+    h::Ptr{Cvoid}
+    net::FeedforwardNetwork
+end
+
+function upload(ctx::Context, net::FeedforwardNetwork)
+    Ws = [Matrix{Float64}(L.weights) for L in net.layers]      # column-major, widened exactly
+    bs = [Vector{Float64}(L.bias) for L in net.layers]
+    dims = Int32[size(Ws[1], 2); [size(W, 1) for W in Ws]]
+    acts = Int32[act_id(L.activation) for L in net.layers]
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve Ws bs begin
+        Wp = [pointer(W) for W in Ws]; bp = [pointer(b) for b in bs]
+        check(ctx, ccall((:clr_net_upload, LIB), Int32,
+                         (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Ref{Ptr{Cvoid}}),
+                         ctx.h, length(Ws), dims, acts, Wp, bp, out))
+    end
+    return DeviceNetwork(out[], net)
+end
+
+# clr_prepost, field for field
+struct PrePost
+    pre_rows::Int32; preA::Ptr{Float64}; preb::Ptr{Float64}
+    post_kind::Int32; post_rows::Int32; postA::Ptr{Float64}; postb::Ptr{Float64}; post_dims::Ptr{Int32}
+end
+PrePost() = PrePost(0, C_NULL, C_NULL, 0, 0, C_NULL, C_NULL, C_NULL)
+
+"""
+Array-backed replacement of `apply(BoxSplitter(partition), X)` (src/splitters.jl:20-28): the tables of
+`split(box_approximation(X), partition)`; cells stay implicit (cell id -> multi-index, dimension 1 fastest).
+"""
+struct BoxGrid
+    partition::Vector{Int32}
+    centers::Vector{Float64}      # concatenated per-dimension tables
+    radii::Vector{Float64}
+end
+
+function BoxGrid(X, partition::AbstractVector{<:Integer})
+    H = box_approximation(X); c = center(H); R = radius_hyperrectangle(H)
+    cs = Float64[]; rs = Float64[]
+    for (i, m) in enumerate(partition)
+        r = R[i] / m
+        append!(cs, m == 1 ? [c[i]] : collect(range(c[i] - R[i] + r; step=2r, length=m)))   # LazySets' split
+        append!(rs, fill(m == 1 ? R[i] : r, m))
+    end
+    return BoxGrid(Int32.(partition), cs, rs)
+end
+Base.length(g::BoxGrid) = prod(Int.(g.partition))
+
+"""
+Batched `controller_forward` (src/solve.jl:210-218) over all cells of a split: replaces the loops at
+src/solve.jl:162-166 and :190-195.  Returns the m x N matrices of `low` / `high` of U per cell; with the default
+`TaylorModelReconstructor(box=true)` (src/setops.jl:76-83) that is everything `_reconstruct` consumes.
+"""
+function controller_forward_boxes(ctx::Context, dnet::DeviceNetwork, g::BoxGrid, pp::PrePost, m::Integer;
+                                  cell_begin::Integer=0, cell_count::Integer=length(g) - cell_begin)
+    lo = Matrix{Float64}(undef, m, cell_count); hi = similar(lo)
+    check(ctx, ccall((:clr_deepz_boxgrid, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ref{PrePost},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Int32, Int32),
+                     ctx.h, dnet.h, length(g.partition), g.partition, g.centers, g.radii, cell_begin, cell_count, pp,
+                     lo, hi, C_NULL, C_NULL, C_NULL, 0, 2 #= CLR_FLAG_NO_STATS =#))
+    return lo, hi
+end
+
+"Same for arbitrary zonotope cells (control steps k > 1: X0s = [set(_project_oa(R, st_vars, t))], src/solve.jl:183-187)."
+function controller_forward_boxes(ctx::Context, dnet::DeviceNetwork, Zs::AbstractVector{<:Zonotope}, pp::PrePost, m::Integer)
+    n = dim(first(Zs)); N = length(Zs)
+    C = reduce(hcat, center.(Zs)); off = Int64[0; cumsum(ngens.(Zs))]; G = reduce(hcat, genmat.(Zs))
+    lo = Matrix{Float64}(undef, m, N); hi = similar(lo)
+    check(ctx, ccall((:clr_deepz_zonotopes, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ref{PrePost},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Int32, Int32),
+                     ctx.h, dnet.h, n, N, C, off, G, pp, lo, hi, C_NULL, C_NULL, C_NULL, 0, 2))
+    return lo, hi
+end
+
+"""
+`simulate`'s period loop (src/simulate.jl:98-140) for a built-in plant: x0 is n_state x N, Wd n_dist x N x iters
+(drawn on the Julia side in the reference's RNG order: x0 once, then W0 once per period, src/simulate.jl:89, :111).
+"""
+function rollout(ctx::Context, dnet::DeviceNetwork, pp::PrePost, plant::Integer, x0::Matrix{Float64}, Wd, t0, τ, T, iters;
+                 n_dist::Integer, n_ctrl::Integer, abstol=1e-6, reltol=1e-3)
+    ns, N = size(x0)
+    Xend = Array{Float64}(undef, ns, N, iters); U = Array{Float64}(undef, n_ctrl, N, iters)
+    check(ctx, ccall((:clr_rollout, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ref{PrePost}, Int32, Int32, Int32, Int32, Int64, Int32, Ptr{Float64}, Ptr{Float64},
+                      Float64, Float64, Float64, Int32, Float64, Float64, Int32, Int32, Ptr{Float64}, Ptr{Float64},
+                      Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int32),
+                     ctx.h, dnet.h, pp, plant, ns, n_dist, n_ctrl, N, iters, x0, n_dist > 0 ? Wd : C_NULL,
+                     t0, τ, T, 0 #= Tsit5 =#, abstol, reltol, 4, 1 #= fastpow =#, Xend, U, C_NULL, C_NULL, 0, C_NULL, C_NULL, C_NULL, 0))
+    return Xend, U
+end
+
+end # module
