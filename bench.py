@@ -120,6 +120,7 @@ def workload(args, world):
 
 def cpu_baseline(net, grid, budget_s=12.0):
     """The C restatement of the reference (oracle/, OpenMP over cells, all host cores) on a bounded sample."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import cbind
     on = cbind.Net(net.as_tuples())
     cores = cbind.num_threads()
@@ -140,6 +141,7 @@ def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun pins it to 1; the CPU arm uses every host core
     net, grid = workload(args, 1)
     from oracle import cbind
     on = cbind.Net(net.as_tuples())
