@@ -146,7 +146,27 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
             const int nbAct = min(NB, (nCols - cg * NB * 8 + 7) >> 3);   // column blocks that hold real columns
             if (mine) {
                 const double* xb = X + (cg * NB * 8 + qr) * P + qc;
-                if (resident) {
+                if (resident && KS == KSREG && nbAct == NB && blkMask == 0xFu) {
+                    // full group, whole row block: no predicates, so the loads run ahead of the tensor pipe
+#pragma unroll
+                    for (int k = 0; k < KSREG; k++) {
+#pragma unroll
+                        for (int j = 0; j < NB; j++) {
+                            const double b = xb[j * 8 * P + k * 4];
+                            dmma884(d[j][0], d[j][1], a[k], b);
+                        }
+                    }
+                } else if (resident && KS == KSREG && bp == NB) {
+                    // shared row block: this warp's single column block of the group
+                    if (myB < nbAct) {
+                        double e0 = 0.0, e1 = 0.0;     // one chain, k ascending: the same sums as every other path
+                        const double* xs = xb + myB * 8 * P;
+#pragma unroll
+                        for (int k = 0; k < KSREG; k++) dmma884(e0, e1, a[k], xs[k * 4]);
+#pragma unroll
+                        for (int j = 0; j < NB; j++) if (j == myB) { d[j][0] = e0; d[j][1] = e1; }
+                    }
+                } else if (resident) {
 #pragma unroll
                     for (int k = 0; k < KSREG; k++) {
                         if (k < KS) {
