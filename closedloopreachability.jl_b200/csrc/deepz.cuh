@@ -114,7 +114,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                                         const unsigned short* colPos, bool addBias, bool inplace,
                                         unsigned long long* bars, unsigned (&phase)[2], int warp, int lane, int nWarps,
                                         double (&a)[KSREG]) {
-    constexpr int NB = 4;                       // column blocks (8 columns each) per group
+    constexpr int NB = DZ_NB;                   // column blocks (8 columns each) per group
     const int RB = L.rblocks, KS = L.ksteps;
     const int CG = (nCols + 8 * NB - 1) / (8 * NB);
     const int rowsW = clr_pad4(L.m);            // rows written (pad rows of W are zero)
@@ -146,7 +146,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
             const int nbAct = min(NB, (nCols - cg * NB * 8 + 7) >> 3);   // column blocks that hold real columns
             if (mine) {
                 const double* xb = X + (cg * NB * 8 + qr) * P + qc;
-                if (resident && KS == KSREG && nbAct == NB && blkMask == 0xFu) {
+                if (resident && KS == KSREG && nbAct == NB && blkMask == ((1u << NB) - 1u)) {
                     // full group, whole row block: no predicates, so the loads run ahead of the tensor pipe
 #pragma unroll
                     for (int k = 0; k < KSREG; k++) {
@@ -156,15 +156,15 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                             dmma884(d[j][0], d[j][1], a[k], b);
                         }
                     }
-                } else if (resident && KS == KSREG && bp == NB) {
-                    // shared row block: this warp's single column block of the group
-                    if (myB < nbAct) {
-                        double e0 = 0.0, e1 = 0.0;     // one chain, k ascending: the same sums as every other path
-                        const double* xs = xb + myB * 8 * P;
+                } else if (resident && KS == KSREG && bp > 1) {
+                    // shared row block: this warp's column blocks of the group, one unpredicated chain each
+                    for (int jj = myB; jj < nbAct; jj += bp) {
+                        double e0 = 0.0, e1 = 0.0;     // k ascending: the same sums as every other path
+                        const double* xs = xb + jj * 8 * P;
 #pragma unroll
                         for (int k = 0; k < KSREG; k++) dmma884(e0, e1, a[k], xs[k * 4]);
 #pragma unroll
-                        for (int j = 0; j < NB; j++) if (j == myB) { d[j][0] = e0; d[j][1] = e1; }
+                        for (int j = 0; j < NB; j++) if (j == jj) { d[j][0] = e0; d[j][1] = e1; }
                     }
                 } else if (resident) {
 #pragma unroll

@@ -69,4 +69,7 @@ __host__ __device__ inline size_t dz_meta_bytes(bool stats) {
     return (b + 15) & ~(size_t)15;
 }
 
+#ifndef DZ_NB
+#define DZ_NB 4         // column blocks per group of the layer product (one barrier phase per group in place)
+#endif
 #define DZ_THREADS 512   // 16 warps, always (4 per SM sub-partition: 128 registers per thread)

@@ -254,3 +254,49 @@ def test_full_size_properties(ctx):
     ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii,
                                   cell_begin=b, cell_count=2000)
     np.testing.assert_allclose(part["lo"][:2000], ref["lo"], rtol=0, atol=BOX_ATOL)
+
+
+def test_quadrotor_c3_4096_cells(ctx):
+    """BASELINE config C3: Quadrotor controller (12 -> 64^3 -> 3, sigmoid), X0 of models/Quadrotor/Quadrotor.jl:98-99
+    split 4^6 (4096 cells, 198 generators per output zonotope).  Blocks of cells are checked against the oracle,
+    all cells through soundness and the hull."""
+    import clr_b200
+    net = load_net("Quadrotor")
+    dn = ctx.upload(net)
+    r = 0.01 * np.array([0.4] * 6 + [0.0] * 6)
+    g = clr_b200.split_box(-r, r, [4] * 6 + [1] * 6)
+    assert len(g) == 4096
+    out = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, hull=True)
+    assert out["stats"]["max_p_out"] == 6 + 3 * 64 and out["stats"]["sum_unstable"] == [4096 * 64] * 3 + [0]
+    on = _oracle().Net(net.as_tuples())
+    for b in range(0, 4096, 512):
+        ref = _oracle().deepz_boxgrid(on, g.partition, g.centers, g.radii, cell_begin=b, cell_count=64)
+        np.testing.assert_allclose(out["lo"][b:b + 64], ref["lo"], rtol=0, atol=BOX_ATOL)
+        np.testing.assert_allclose(out["hi"][b:b + 64], ref["hi"], rtol=0, atol=BOX_ATOL)
+    rng = np.random.default_rng(3)
+    ids = rng.integers(0, 4096, 500)
+    X = np.array([g.cell(int(i))[0] + g.cell(int(i))[1] * rng.uniform(-1, 1, 12) for i in ids])
+    U = ctx.forward_points(dn, X)
+    assert np.all(U >= out["lo"][ids] - 1e-12) and np.all(U <= out["hi"][ids] + 1e-12)
+    np.testing.assert_array_equal(out["hull_lo"], out["lo"].min(0))
+
+
+def test_tora_c2_ten_control_periods(ctx):
+    """BASELINE config C2: TORA, 10^3 cells per step, 10 control periods: k = 1 is the box split of X0, k > 1 are
+    10^3 synthetic zonotopes per step (n = 4, p0 = 10)."""
+    import clr_b200
+    from clr_b200 import workloads
+    net = load_net("TORA_ReLU")
+    dn = ctx.upload(net)
+    on = _oracle().Net(net.as_tuples())
+    g = clr_b200.split_box(TORA_LO, TORA_HI, [10, 10, 10, 1])
+    got = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, post=("shift", -10.0))
+    ref = _oracle().deepz_boxgrid(on, g.partition, g.centers, g.radii, post=("shift", -10.0))
+    _cmp_boxes(got, ref)
+    rng = np.random.default_rng(12)
+    for k in range(2, 11):
+        C, off, G = workloads.random_zonotopes(rng, 1000, 4, 10, 10, -0.7, 0.7, 0.9 ** k * 0.02)
+        got = ctx.deepz_zonotopes(dn, C, off, G, post=("shift", -10.0))
+        ref = _oracle().deepz_zonotopes(on, C, off, G, post=("shift", -10.0))
+        _cmp_boxes(got, ref)
+        assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"]
