@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclr_b200.so")
+LIB_PATH = os.environ.get("CLR_B200_LIB") or os.path.join(_HERE, "libclr_b200.so")
 MAX_LAYERS = 32
 
 # every symbol include/clr_b200.h declares (tests check the export list against the header)

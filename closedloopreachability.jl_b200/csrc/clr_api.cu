@@ -658,6 +658,13 @@ int32_t clr_last_pass_info(clr_ctx* ctx, double* pass_ms, int64_t* retried, int6
     return 0;
 }
 
+// DZ_TIMING builds only: cycles per phase of the last DeepZ call, summed over CTAs (not part of the public header)
+int32_t clr_debug_timers(clr_ctx* ctx, unsigned long long* out8) {
+    if (!ctx || !out8) return CLR_ERR_ARG;
+    for (int i = 0; i < 8; i++) out8[i] = ctx->h_state->timers[i];
+    return 0;
+}
+
 int32_t clr_net_upload(clr_ctx* ctx, int32_t n_layers, const int32_t* dims, const int32_t* act,
                        const double* const* W, const double* const* b, clr_net** out) {
     if (!ctx) return CLR_ERR_ARG;

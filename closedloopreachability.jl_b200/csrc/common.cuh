@@ -59,6 +59,7 @@ struct DevCallState {
     unsigned long long next_big;       // cursor of the global-store pass
     unsigned long long n_retry;        // cells in the retry list
     unsigned long long n_big;          // cells in the big-cell list
+    unsigned long long timers[8];      // DZ_TIMING builds: cycles per phase (input, product, appended, relax, layout, output, fetch, other)
 };
 
 __host__ __device__ inline int clr_pad4(int x) { return (x + 3) & ~3; }

@@ -27,6 +27,12 @@
 #pragma once
 #include "deepz_types.cuh"
 
+#ifdef DZ_TIMING
+#define DZ_T(i) do { if (tid == 0) { long long tn_ = clock64(); tacc[i] += tn_ - tlast; tlast = tn_; } } while (0)
+#else
+#define DZ_T(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
@@ -139,7 +145,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
         unsigned blkMask = 0;
         for (int j = 0; j < NB; j++) if ((j % bp) == myB) blkMask |= 1u << j;
         for (int cg = CG - 1; cg >= 0; cg--) {
-            const bool mine = active && partOk && (cg % gp) == myG;
+            const bool mine = active && partOk && (gp == 1 || (cg % gp) == myG);
             double d[NB][2];
 #pragma unroll
             for (int j = 0; j < NB; j++) { d[j][0] = 0.0; d[j][1] = 0.0; }
@@ -192,6 +198,16 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                     }
                 }
             }
+            // target columns of this thread's results: looked up before the barrier so that the wait hides the latency
+            unsigned pos[NB][2];
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int col = cg * NB * 8 + j * 8 + qc * 2 + e;
+                    pos[j][e] = (mine && col < nCols && ((blkMask >> j) & 1u)) ? colPos[col] : 0xFFFFu;
+                }
+            }
             if (inplace) {
                 // everybody has read group cg (and all groups behind it): only then may its results, which land
                 // at or behind column 32 cg, be written
@@ -206,14 +222,10 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                 for (int j = 0; j < NB; j++) {
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        const int col = cg * NB * 8 + j * 8 + qc * 2 + e;
-                        if (col < nCols && ((blkMask >> j) & 1u)) {
-                            const unsigned pos = colPos[col];
-                            if (pos != 0xFFFFu) {
-                                double v = d[j][e];
-                                if (addBias && (pos & 0x8000u)) v += bias;
-                                Y[(pos & 0x7FFFu) * P + row] = v;
-                            }
+                        if (pos[j][e] != 0xFFFFu) {
+                            double v = d[j][e];
+                            if (addBias && (pos[j][e] & 0x8000u)) v += bias;
+                            Y[(pos[j][e] & 0x7FFFu) * P + row] = v;
                         }
                     }
                 }
@@ -340,6 +352,10 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         pfFirst = atomicAdd(cursor, (unsigned long long)pfT);
     }
     __syncthreads();
+#ifdef DZ_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#endif
     unsigned phase[2] = {0u, 0u};
     double a[KSREG];
 #pragma unroll
@@ -369,6 +385,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
         }
         __syncthreads();
+        DZ_T(6);
         if (!S.more) break;
         int nCells = S.nCells;
         // store geometry of this tile: [columns ... | staging (nCells x stageW)]
@@ -443,17 +460,34 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             const int rows4 = clr_pad4(n);
             const int* colOff = S.colOff[0];
             if (in.kind == 0) {
-                for (int it = tid; it < nCells * rows4; it += NT) {
-                    const int ci = it / rows4, d = it - ci * rows4;
-                    const int cb = colOff[ci], p = S.wUsed[0][ci] - 1;
-                    double c = 0.0, r = 0.0;
-                    int rank = 0;
-                    if (d < n) {
-                        c = tmpC[ci * n + d]; r = tmpR[ci * n + d];
-                        for (int dd = 0; dd < d; dd++) rank += tmpR[ci * n + dd] != 0.0;
+                // Box cells: the generators are r_d * e_d, so the first layer needs no tensor product: its output is
+                // W c (summed over d in ascending order, like the reference's affine map) and the columns r_d * W[:, d].
+                const DevLayer& L0 = S.layers[0];
+                const int m0 = L0.m, rowsP0 = clr_pad4(m0);
+                const bool bias0 = L0.act == CLR_ACT_ID && !L0.collapse;     // no relaxation follows: bias goes in here
+                double* dst = inplace ? cur : oth;
+                const int G0 = NT / rowsP0, slot = tid / rowsP0, r = tid - slot * rowsP0;
+                if (slot < G0) {
+                    for (int ci = slot; ci < nCells; ci += G0) {
+                        const int cb = colOff[ci];
+                        double* y = dst + cb * P + r;
+                        if (r < m0) {
+                            const double* cc = tmpC + ci * n;
+                            const double* rr = tmpR + ci * n;
+                            double sacc = 0.0;
+                            int j = 1;
+                            for (int d = 0; d < n; d++) {
+                                const double wv = __ldg(L0.Wcm + (size_t)d * m0 + r);
+                                sacc += wv * cc[d];
+                                const double rd = rr[d];
+                                if (rd != 0.0) { y[j * P] = wv * rd; j++; }
+                            }
+                            y[0] = bias0 ? sacc + __ldg(L0.bias + r) : sacc;
+                        } else {
+                            const int w = S.wUsed[0][ci];
+                            for (int j = 0; j < w; j++) y[j * P] = 0.0;
+                        }
                     }
-                    cur[cb * P + d] = c;
-                    for (int j = 0; j < p; j++) cur[(cb + 1 + j) * P + d] = (r != 0.0 && j == rank) ? r : 0.0;
                 }
             } else {
                 for (int it = tid; it < nCells * rows4; it += NT) {
@@ -472,6 +506,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
             __syncthreads();   // input store and position table complete
         }
+        DZ_T(0);
 
         // ---- layers ------------------------------------------------------------------------------------------------
         // invariant at the top (parity `flip`): data in layout colOff[flip] with wUsed[flip] columns per cell, generators
@@ -496,7 +531,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             const int act = Ly.act, collapse = Ly.collapse;
             const bool relax = !(act == CLR_ACT_ID && !collapse);
             const int m = Ly.m, rowsP = clr_pad4(m), mw = (m + 31) >> 5;
-            dz_gemm<KSREG>(Ly, cur, oth, P, nCols, S.colPos, !relax, inplace, S.bar, phase, warp, lane, nWarps, a);
+            if (!(l == 0 && in.kind == 0))   // box cells enter with the first layer's product already applied
+                dz_gemm<KSREG>(Ly, cur, oth, P, nCols, S.colPos, !relax, inplace, S.bar, phase, warp, lane, nWarps, a);
+            DZ_T(1);
             // Pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i].  In place this is safe
             // without another barrier: the last mbarrier phase of the sweep means every warp has read every column.
             if (l > 0) {
@@ -546,6 +583,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
             { double* tp = cur; cur = oth; oth = tp; }
             __syncthreads();   // [1] all columns moved to layout colOff[flip ^ 1]; pending generators materialised
+            DZ_T(2);
             const int* colOff = S.colOff[flip ^ 1];
 
             // ---- relaxation: bounds, lambda, mu, rows scaled in place; thread = (cell slot, row) ------------------------
@@ -604,6 +642,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 }
                 __syncthreads();   // [2]
             }
+            DZ_T(3);
             // ---- next layout (every warp computes it; warp 0 publishes it) and the position table -----------------------
             {
                 int off0, off1, keep, total;
@@ -687,6 +726,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
             nCols = colOff[nCells];          // columns of the current layout that the next product reads
             __syncthreads();   // [3] next layout, position table and widths published
+            DZ_T(4);
             if (needDead) {
                 if (Ly.remove_zero) dz_mark_dead(S.deadMask[flipD], colOff, S.wUsed[flip], cur, P, m, nCells, tid, NT);
                 else if (relax) { for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) S.deadMask[flipD][i] = 0; __syncthreads(); }
@@ -774,6 +814,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 }
             }
         }
+        DZ_T(5);
         // ---- adapt the tile size to the growth just seen ---------------------------------------------------------------
         if (tid == 0) {
             if (sp.tile_cells <= 0 && sp.pass != 2) {
@@ -788,6 +829,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         __syncthreads();
     }
 
+#ifdef DZ_TIMING
+    if (tid == 0) for (int i = 0; i < 8; i++) atomicAdd(&st->timers[i], (unsigned long long)tacc[i]);
+#endif
     // ---- per-CTA accumulators -> global -----------------------------------------------------------------------------------
     __syncthreads();
     if (STATS) {
