@@ -104,6 +104,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(regime):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one main-pass launch of this workload (ncu --set full capture
+    committed under profiles/; the boxes written by the launch stay in the 126 MB L2 at this size)."""
+    try:
+        if regime != "stable":
+            return None
+        with open(os.path.join(ROOT, "profiles", "r01", "ncu_deepz_bench_launch.json")) as fh:
+            return json.load(fh)["traffic"]
+    except Exception:
+        return None
+
+
 def workload(args, world):
     """C4: box [c0-s, c0+s]^6 split [10]^6; with N ranks the box is N times longer in the last (slowest)
     dimension and split 10 N times there, so every rank owns 10^6 cells of identical size."""
@@ -272,7 +284,7 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": ["deepz_kernel (main pass, smem store)", "deepz_kernel (retry pass)",
                                               "deepz_kernel (big-cell pass, global store)"][dom],
                 "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / DMMA_PEAK_TFLOPS,
-                "traffic": None,
+                "traffic": ncu_traffic(args.regime),
                 "peak_source": "FP64 mma.sync (DMMA) issue peak measured on this pool's B200 "
                                "(profiles/microbench/r01_dmma_bench_b200.txt; cuBLAS DGEMM 8192^3 = 35.5); "
                                "MEASURED_PEAKS.json has no FP64 entry",
