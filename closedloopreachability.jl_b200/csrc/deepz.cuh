@@ -162,8 +162,8 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                             dmma884(d[j][0], d[j][1], a[k], b);
                         }
                     }
-                } else if (resident && KS == KSREG && bp > 1) {
-                    // shared row block: this warp's column blocks of the group, one unpredicated chain each
+                } else if (resident && KS == KSREG) {
+                    // shared row block or partial group: this warp's column blocks, one unpredicated chain each
                     for (int jj = myB; jj < nbAct; jj += bp) {
                         double e0 = 0.0, e1 = 0.0;     // k ascending: the same sums as every other path
                         const double* xs = xb + jj * 8 * P;
