@@ -6,8 +6,8 @@ The compute lives in ``libclr_b200.so`` (CUDA, sm_100a); see ``include/clr_b200.
 """
 from .network import DenseLayerOp, FeedforwardNetwork, ACT_IDS  # noqa: F401
 from .polar import read_POLAR  # noqa: F401
-from .splitters import (BoxGrid, BoxSplitter, IndexedSplitter, NoSplitter, Splitter, julia_range,  # noqa: F401
-                        split_box)
+from .splitters import (BoxGrid, BoxSplitter, IndexedSplitter, NoSplitter, SignSplitter, Splitter,  # noqa: F401
+                        ZonotopeCells, ZonotopeSplitter, julia_range, split_box, split_zonotope)
 
 
 def __getattr__(name):

@@ -169,3 +169,65 @@ class IndexedSplitter:
 
     def __getitem__(self, k: int):
         return self.index2splitter[k]
+
+
+@dataclass
+class ZonotopeCells:
+    """A batch of zonotope cells in the layout clr_deepz_zonotopes takes: centres (N, n), generator offsets (N+1,),
+    generators (sum p, n) -- row j is generator j."""
+    C: np.ndarray
+    col_off: np.ndarray
+    G: np.ndarray
+
+    def __len__(self) -> int:
+        return self.C.shape[0]
+
+    def cell(self, i: int):
+        return self.C[i], self.G[self.col_off[i]:self.col_off[i + 1]].T
+
+
+def split_zonotope(c, G, gens, nparts) -> ZonotopeCells:
+    """LazySets ``split(Z, gens, nparts)``: generator ``gens[i]`` (0-based here) is halved ``nparts[i]`` times; every
+    halving replaces each zonotope Z by (Z - g/2, Z + g/2) with that generator halved, in this order, so the result
+    has 2^sum(nparts) cells (src/splitters.jl:30-43 passes the user's arguments straight through)."""
+    c = np.asarray(c, dtype=np.float64)
+    G = np.asarray(G, dtype=np.float64).reshape(len(c), -1)
+    if len(gens) != len(nparts):
+        raise ValueError("gens and nparts must have the same length")
+    cs = c[None, :].copy()
+    Gc = G.copy()                      # all cells share the generator matrix, only the centres differ
+    for g, times in zip(gens, nparts):
+        if not (0 <= g < Gc.shape[1]):
+            raise ValueError(f"generator index {g} out of range")
+        for _ in range(int(times)):
+            half = Gc[:, g] / 2
+            cs = np.stack([cs - half, cs + half], axis=1).reshape(-1, len(c))   # (Z1a, Z1b, Z2a, Z2b, ...)
+            Gc[:, g] = half
+    N, p = cs.shape[0], Gc.shape[1]
+    return ZonotopeCells(np.ascontiguousarray(cs), np.arange(N + 1, dtype=np.int64) * p,
+                         np.ascontiguousarray(np.tile(Gc.T, (N, 1))))
+
+
+class ZonotopeSplitterFun:
+    def __init__(self, generators=None, splits=None):
+        self.generators, self.splits = generators, splits
+
+    def __call__(self, c, G):
+        G = np.asarray(G, dtype=np.float64).reshape(len(c), -1)
+        if self.generators is None and self.splits is None:       # default: one split per generator
+            return split_zonotope(c, G, list(range(G.shape[1])), [1] * G.shape[1])
+        return split_zonotope(c, G, self.generators, self.splits)
+
+
+def ZonotopeSplitter(generators=None, splits=None) -> Splitter:
+    """``ZonotopeSplitter`` of the reference (src/splitters.jl:30-43); ``apply(c, G)`` returns ZonotopeCells."""
+    return Splitter(ZonotopeSplitterFun(generators, splits))
+
+
+class SignSplitter:
+    """``SignSplitter`` (src/splitters.jl:60-71): an interval containing 0 in its interior is cut at 0."""
+
+    def apply(self, lo: float, hi: float):
+        if lo < 0.0 and hi > 0.0:
+            return [(lo, 0.0), (0.0, hi)]
+        return [(lo, hi)]

@@ -411,3 +411,26 @@ def deepz_boxgrid(net, lo, hi, partition, pre=None, post=None, cell_range=None, 
 def algorithmic_flops(net, p_in):
     """F = sum_l 2*m_l*n_l*(p_l + 1), p_l = generator columns entering layer l."""
     return sum(2 * W.shape[0] * W.shape[1] * (p + 1) for (W, _, _), p in zip(net, p_in))
+
+
+# --------------------------------------------------------------------------------------
+# ZonotopeSplitter -> LazySets.split(Z, gens, nparts)       (src/splitters.jl:30-43) [UPSTREAM-RECALL]
+# --------------------------------------------------------------------------------------
+def split_zonotope_once(c, G, j):
+    """split(Z, j): (Zonotope(c - g_j/2, G'), Zonotope(c + g_j/2, G')) with G' = G, column j halved."""
+    G2 = G.copy()
+    G2[:, j] = G[:, j] / 2
+    return (c - G2[:, j], G2), (c + G2[:, j], G2)
+
+
+def split_zonotope(c, G, gens, nparts):
+    """Recursive restatement: every round replaces each zonotope by its two halves, in order."""
+    Zs = [(np.asarray(c, dtype=np.float64), np.asarray(G, dtype=np.float64))]
+    for g, times in zip(gens, nparts):
+        for _ in range(times):
+            nxt = []
+            for (cc, GG) in Zs:
+                a, b = split_zonotope_once(cc, GG, g)
+                nxt += [a, b]
+            Zs = nxt
+    return Zs

@@ -300,3 +300,18 @@ def test_tora_c2_ten_control_periods(ctx):
         ref = _oracle().deepz_zonotopes(on, C, off, G, post=("shift", -10.0))
         _cmp_boxes(got, ref)
         assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"]
+
+
+def test_zonotope_splitter_cells(ctx):
+    """ZonotopeSplitter cells (src/splitters.jl:30-43) go through clr_deepz_zonotopes like any other cell batch."""
+    import clr_b200
+    net = load_net("TORA_ReLU")
+    rng = np.random.default_rng(9)
+    c = np.array([0.65, -0.65, -0.35, 0.55])
+    G = np.hstack([np.diag([0.05] * 4), 1e-3 * rng.uniform(-1, 1, (4, 3))])
+    cells = clr_b200.ZonotopeSplitter([0, 1, 2, 4], [2, 2, 1, 1]).apply(c, G)
+    assert len(cells) == 64
+    got = ctx.deepz_zonotopes(ctx.upload(net), cells.C, cells.col_off, cells.G, post=("shift", -10.0), hull=True)
+    ref = _oracle().deepz_zonotopes(_oracle().Net(net.as_tuples()), cells.C, cells.col_off, cells.G, post=("shift", -10.0))
+    _cmp_boxes(got, ref)
+    assert got["hull_lo"][0] == got["lo"].min() and got["hull_hi"][0] == got["hi"].max()

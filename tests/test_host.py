@@ -163,3 +163,25 @@ def test_two_rank_sharding_over_gloo(tmp_path):
                          env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_zonotope_and_sign_splitters():
+    import clr_b200
+    from oracle import deepz_np as dz
+    rng = np.random.default_rng(4)
+    c, G = rng.uniform(-1, 1, 4), rng.uniform(-0.3, 0.3, (4, 5))
+    cells = clr_b200.split_zonotope(c, G, [0, 3], [2, 1])
+    ref = dz.split_zonotope(c, G, [0, 3], [2, 1])
+    assert len(cells) == len(ref) == 8
+    for i, (rc, rG) in enumerate(ref):
+        cc, GG = cells.cell(i)
+        assert np.array_equal(cc, rc) and np.array_equal(GG, rG)          # same cells, same order
+    # the cells cover the original zonotope: every vertex combination of the split generators is reproduced
+    default = clr_b200.ZonotopeSplitter().apply(c, G)                     # one split per generator
+    assert len(default) == 2 ** 5
+    lo = (default.C - np.abs(default.G.reshape(32, 5, 4)).sum(1)).min(0)
+    np.testing.assert_allclose(lo, c - np.abs(G).sum(1), rtol=1e-14)
+    with pytest.raises(ValueError):
+        clr_b200.split_zonotope(c, G, [7], [1])
+    s = clr_b200.SignSplitter()
+    assert s.apply(-1.0, 2.0) == [(-1.0, 0.0), (0.0, 2.0)] and s.apply(0.0, 2.0) == [(0.0, 2.0)]
