@@ -9,6 +9,10 @@ from .polar import read_POLAR  # noqa: F401
 from .splitters import (BoxGrid, BoxSplitter, IndexedSplitter, NoSplitter, SignSplitter, Splitter,  # noqa: F401
                         ZonotopeCells, ZonotopeSplitter, julia_range, split_box, split_zonotope)
 
+from .problem import (AffinePreprocessing, ControlledPlant, LinearMapPostprocessing, NoPostprocessing,  # noqa: F401
+                      NoPreprocessing, ProjectionPostprocessing, UniformAdditivePostprocessing, controller_forward)
+from .simulate import EnsembleSimulationSolution, SimulationSolution, sample_box, simulate  # noqa: F401
+
 
 def __getattr__(name):
     # the CUDA-backed parts are imported lazily so that pure-host helpers work before build()

@@ -107,3 +107,30 @@ def test_unicycle_c5_full_size(ctx):
     b, e = 375000, 500000                                  # rank 3 of 8
     part = ctx.rollout(dn, "Unicycle", x0[b:e], Wd[:, b:e], 0.0, 0.2, 10.0, iters, post=("shift", -20.0), counts=False)
     assert np.array_equal(part["X_end"], got["X_end"][:, b:e]) and np.array_equal(part["U"], got["U"][:, b:e])
+
+
+def test_simulate_mirror(ctx):
+    """simulate(prob; T, trajectories, include_vertices) (src/simulate.jl:68-143) on the Unicycle model
+    (models/Unicycle/Unicycle.jl:34-80) against the oracle fed with the same samples."""
+    import clr_b200
+    net = load_net("Unicycle")
+    vars_ = {"states": [1, 2, 3, 4], "disturbances": [5], "controls": [6, 7]}
+    lo = [9.5, -4.5, 2.1, 1.5, -1e-4, 0.0, 0.0]
+    hi = [9.55, -4.45, 2.11, 1.51, 1e-4, 0.0, 0.0]
+    prob = clr_b200.ControlledPlant("Unicycle", lo, hi, net, vars_, 0.2,
+                                    postprocessing=clr_b200.UniformAdditivePostprocessing(-20.0))
+    sol = clr_b200.simulate(ctx, prob, T=1.5, trajectories=40, include_vertices=True, rng=np.random.default_rng(3),
+                            save_steps=True)
+    assert len(sol) == 40 + 16                       # the vertices of X0 are appended (src/simulate.jl:89-90)
+    iters = 8                                        # ceil(1.5 / 0.2); the last period is shorter
+    assert sol.X_end.shape == (iters, 56, 4) and sol.controls().shape == (56, iters, 2)
+    ref = _oracle().rollout(_oracle().Net(net.as_tuples()), "Unicycle", 4, 1, 2, sol.x0, sol.Wd, 0.0, 0.2, 1.5, iters,
+                            post=("shift", -20.0))
+    np.testing.assert_allclose(sol.X_end, ref["X_end"], rtol=0, atol=TRAJ_ATOL)
+    one = sol[3]
+    assert len(one) == iters and one.controls().shape == (iters, 2) and one.disturbances().shape == (iters, 1)
+    t_last, u_last = one.trajectory()[-1]
+    assert abs(t_last[-1] - 1.5) < 1e-15 and u_last.shape[1] == 7
+    np.testing.assert_allclose(u_last[-1, :4], sol.X_end[-1, 3], rtol=0, atol=1e-15)
+    with pytest.raises(ValueError):
+        clr_b200.simulate(ctx, prob, trajectories=4)

@@ -185,3 +185,32 @@ def test_zonotope_and_sign_splitters():
         clr_b200.split_zonotope(c, G, [7], [1])
     s = clr_b200.SignSplitter()
     assert s.apply(-1.0, 2.0) == [(-1.0, 0.0), (0.0, 2.0)] and s.apply(0.0, 2.0) == [(0.0, 2.0)]
+
+
+def test_controlled_plant_and_processing_mirror():
+    """apply() semantics of src/problem.jl:5-77 on vectors and the dimension check of src/solve.jl:130-134."""
+    import clr_b200
+    u = np.array([1.0, -2.0, 3.0])
+    assert np.array_equal(clr_b200.NoPostprocessing().apply(u), u)
+    assert np.array_equal(clr_b200.UniformAdditivePostprocessing(-10.0).apply(u), u - 10.0)
+    assert np.array_equal(clr_b200.ProjectionPostprocessing([3, 1]).apply(u), [3.0, 1.0])      # 1-based like Julia
+    assert np.array_equal(clr_b200.LinearMapPostprocessing(11.0).apply(u), 11.0 * u)
+    M = np.array([[1.0, 0.0, 2.0]])
+    assert np.array_equal(clr_b200.LinearMapPostprocessing(M).apply(u), M @ u)
+    assert clr_b200.ProjectionPostprocessing([3, 1]).as_arg() == ("project", [2, 0])
+    with pytest.warns(UserWarning):
+        clr_b200.UniformAdditivePostprocessing(0.0)                                           # src/problem.jl:16-19
+    pre = clr_b200.AffinePreprocessing(np.eye(2), [1.0, 2.0])
+    assert np.array_equal(pre.apply([1.0, 1.0]), [2.0, 3.0])
+    net = load_net("Unicycle")
+    vars_ = {"states": [1, 2, 3, 4], "disturbances": [5], "controls": [6, 7]}
+    lo = [9.5, -4.5, 2.1, 1.5, -1e-4, 0.0, 0.0]
+    hi = [9.55, -4.45, 2.11, 1.51, 1e-4, 0.0, 0.0]
+    prob = clr_b200.ControlledPlant("Unicycle", lo, hi, net, vars_, 0.2,
+                                    postprocessing=clr_b200.UniformAdditivePostprocessing(-20.0))
+    assert prob.states() == [1, 2, 3, 4] and prob.disturbances() == [5] and prob.controls() == [6, 7]
+    assert np.array_equal(prob.project(prob.disturbances())[0], [-1e-4])
+    with pytest.raises(ValueError):
+        clr_b200.ControlledPlant("Unicycle", lo[:6], hi[:6], net, vars_, 0.2)
+    x = clr_b200.sample_box(np.random.default_rng(0), lo[:4], hi[:4], 5, include_vertices=True)
+    assert x.shape == (5 + 16, 4) and np.all(x >= np.array(lo[:4])) and np.all(x <= np.array(hi[:4]))
