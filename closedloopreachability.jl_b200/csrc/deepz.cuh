@@ -211,11 +211,8 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
             if (inplace) {
                 // everybody has read group cg (and all groups behind it): only then may its results, which land
                 // at or behind column 32 cg, be written
-                unsigned long long* bar = bars + (cg & 1);
-                __syncwarp();
-                if (lane == 0) dz_mbar_arrive(bar);
-                dz_mbar_wait(bar, phase[cg & 1]);
-                phase[cg & 1] ^= 1u;
+                // (a hardware named barrier: ~10x lower latency than an mbarrier phase with try_wait here)
+                asm volatile("bar.sync 1, %0;\n" ::"r"(nWarps * 32) : "memory");
             }
             if (mine && row < rowsW) {
 #pragma unroll
