@@ -10,8 +10,8 @@
 //     (mma.sync.m8n8k4.f64 -> SASS DMMA; tcgen05 has no FP64 kind): a warp owns 8 output rows,
 //     keeps their W fragments in registers and streams the columns as B fragments from smem.  The
 //     sweep goes over the column groups back to front; results are written to the columns' positions
-//     in the NEXT layout (cells only ever move right, making room for appended generators), and an
-//     mbarrier phase per column group keeps writers behind all readers;
+//     in the NEXT layout (cells only ever move right, making room for appended generators), and a
+//     named barrier per column group keeps writers behind all readers;
 //   * generators appended by the previous relaxation are mu * e_i: their image under W is mu * W[:, i],
 //     so they never go through the tensor pipe -- they are materialised as scaled weight columns;
 //   * the interval bounds (sequential |.| row sums, same order as LazySets low/high), the
@@ -37,22 +37,6 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
-}
-
-// ---- mbarrier (shared memory barrier with phases): split arrive / wait for the in-place sweep -----------
-__device__ __forceinline__ unsigned dz_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void dz_mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(dz_smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void dz_mbar_arrive(unsigned long long* bar) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(dz_smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void dz_mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n .reg .pred p;\n"
-        "W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        " @!p bra W_%=;\n}\n" ::"r"(dz_smem_addr(bar)), "r"(parity)
-        : "memory");
 }
 
 __device__ __forceinline__ bool dz_approxzero(double x) { return fabs(x) <= CLR_ZTOL; }
@@ -112,13 +96,13 @@ __device__ __forceinline__ void dz_load_a(const DevLayer& L, int warp, int lane,
 
 // ---------------------------------------------------------------------------------------------
 // Layer product.  Column j of X (current layout) goes to column colPos[j] of Y (next layout);
-// Y == X when `inplace` (then the groups are swept back to front under the mbarrier protocol).
+// Y == X when `inplace` (then the groups are swept back to front, one named barrier per group).
 // Bias is added by the relaxation, or here on the centre columns for layers without one.
 // ---------------------------------------------------------------------------------------------
 template <int KSREG>
 __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, double* Y, int P, int nCols,
                                         const unsigned short* colPos, bool addBias, bool inplace,
-                                        unsigned long long* bars, unsigned (&phase)[2], int warp, int lane, int nWarps,
+                                        int warp, int lane, int nWarps,
                                         double (&a)[KSREG]) {
     constexpr int NB = DZ_NB;                   // column blocks (8 columns each) per group
     const int RB = L.rblocks, KS = L.ksteps;
@@ -320,7 +304,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
     const bool needDead = STATS || out.keep_cap > 0;
     const int stageW = max(clr_pad4(net->max_rows), 2 * n);   // doubles of staging per cell
 
-    // ---- one-time setup: layer descriptors to smem, accumulators, barriers, the first tile ------------------
+    // ---- one-time setup: layer descriptors to smem, accumulators, the first tile ------------------
     for (int i = tid; i < L * (int)(sizeof(DevLayer) / sizeof(int)); i += NT) ((int*)S.layers)[i] = ((const int*)net->layer)[i];
     if (tid < CLR_MAX_LAYERS) { S.sPin[tid] = 0; S.sUnst[tid] = 0; }
     if (tid < CLR_HULL_MAX) { S.hlo[tid] = INFINITY; S.hhi[tid] = -INFINITY; }
@@ -331,8 +315,6 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
     unsigned long long pfFirst = 0;   // thread 0: prefetched tile
     int pfT = 0;
     if (tid == 0) {
-        dz_mbar_init(&S.bar[0], nWarps);
-        dz_mbar_init(&S.bar[1], nWarps);
         int t0 = sp.tile_cells;
         if (t0 <= 0) {
             int guessCols = in.kind == 0 ? in.n + 1 : 8;
@@ -353,7 +335,6 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #endif
-    unsigned phase[2] = {0u, 0u};
     double a[KSREG];
 #pragma unroll
     for (int k = 0; k < KSREG; k++) a[k] = 0.0;
@@ -529,18 +510,47 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             const bool relax = !(act == CLR_ACT_ID && !collapse);
             const int m = Ly.m, rowsP = clr_pad4(m), mw = (m + 31) >> 5;
             if (!(l == 0 && in.kind == 0))   // box cells enter with the first layer's product already applied
-                dz_gemm<KSREG>(Ly, cur, oth, P, nCols, S.colPos, !relax, inplace, S.bar, phase, warp, lane, nWarps, a);
+                dz_gemm<KSREG>(Ly, cur, oth, P, nCols, S.colPos, !relax, inplace, warp, lane, nWarps, a);
             DZ_T(1);
             // Pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i].  In place this is safe
-            // without another barrier: the last mbarrier phase of the sweep means every warp has read every column.
+            // without another barrier: after the last group's barrier of the sweep every warp has read every column.
             if (l > 0) {
                 const int nIt = S.nItems;
                 if (nIt <= DZ_ITEMS_MAX) {
-                    for (int t = warp; t < nIt; t += nWarps) {
-                        const int i = S.itemRow[t], col = S.itemCol[t];
-                        const double mu = stage[S.itemCell[t] * stageW + i];
-                        const double* wc = Ly.Wcm + (size_t)i * m;
-                        for (int r = lane; r < rowsP; r += 32) oth[col * P + r] = r < m ? mu * __ldg(wc + r) : 0.0;
+                    if (rowsP <= 128) {
+                        // all loads of a column (and of the warp's next item) in flight before the stores
+                        for (int t = warp; t < nIt; t += 2 * nWarps) {
+                            const int t2 = t + nWarps;
+                            const bool two = t2 < nIt;
+                            const int i0 = S.itemRow[t], c0 = S.itemCol[t];
+                            const int i1 = two ? S.itemRow[t2] : i0, c1 = two ? S.itemCol[t2] : c0;
+                            const double mu0 = stage[S.itemCell[t] * stageW + i0];
+                            const double mu1 = two ? stage[S.itemCell[t2] * stageW + i1] : 0.0;
+                            const double* w0 = Ly.Wcm + (size_t)i0 * m;
+                            const double* w1 = Ly.Wcm + (size_t)i1 * m;
+                            double v0[4], v1[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int r = lane + 32 * q;
+                                v0[q] = r < m ? __ldg(w0 + r) : 0.0;
+                                v1[q] = (two && r < m) ? __ldg(w1 + r) : 0.0;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int r = lane + 32 * q;
+                                if (r < rowsP) {
+                                    oth[c0 * P + r] = mu0 * v0[q];
+                                    if (two) oth[c1 * P + r] = mu1 * v1[q];
+                                }
+                            }
+                        }
+                    } else {
+                        for (int t = warp; t < nIt; t += nWarps) {
+                            const int i = S.itemRow[t], col = S.itemCol[t];
+                            const double mu = stage[S.itemCell[t] * stageW + i];
+                            const double* wc = Ly.Wcm + (size_t)i * m;
+                            for (int r = lane; r < rowsP; r += 32) oth[col * P + r] = r < m ? mu * __ldg(wc + r) : 0.0;
+                        }
                     }
                 } else {
                     const int mwPrev = (S.layers[l - 1].m + 31) >> 5;

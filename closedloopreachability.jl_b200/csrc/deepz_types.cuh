@@ -42,7 +42,6 @@ struct DeepzSched {
 #define DZ_ITEMS_MAX 384   // pending generators listed per tile (more: the slow walk over the masks)
 
 struct DeepzSmem {
-    unsigned long long bar[2];                // mbarriers of the in-place layer product (one phase per column group)
     int nCells, tileT, more;
     int sMaxP;
     long long firstIdx;
@@ -70,6 +69,6 @@ __host__ __device__ inline size_t dz_meta_bytes(bool stats) {
 }
 
 #ifndef DZ_NB
-#define DZ_NB 4         // column blocks per group of the layer product (one barrier phase per group in place)
+#define DZ_NB 4         // column blocks per group of the layer product (one barrier per group in place)
 #endif
 #define DZ_THREADS 512   // 16 warps, always (4 per SM sub-partition: 128 registers per thread)
