@@ -640,6 +640,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         }
                         y[0] = cn;
                         if (collapse) y[P] = la * rad;       // LazySets' one-row linear_map: a single generator
+                        else if (la == 0.0) { for (int j = 1; j < w; j++) y[j * P] = 0.0; }     // inactive row: exactly zero, no reads
                         else if (la != 1.0) { for (int j = 1; j < w; j++) y[j * P] = y[j * P] * la; }
                         if (unst) {
                             stage[ci * stageW + r] = mm;
