@@ -12,7 +12,7 @@
  *  - every function returns 0 on success and a negative clr_status on error; the message is
  *    available from clr_last_error(); no C++ exception crosses the boundary;
  *  - a clr_ctx is bound to ONE CUDA device and is not thread-safe (one ctx per host task);
- *    calls block the calling thread unless CLR_FLAG_DEVICE_IO is set;
+ *    calls block the calling thread (with CLR_FLAG_DEVICE_IO no bulk data is copied, see the flag);
  *  - there is no CPU fallback: without a CUDA device clr_create fails with CLR_ERR_CUDA.
  *
  * Reference interface replaced by each entry point (paths relative to the reference repo):
@@ -59,8 +59,11 @@ enum { CLR_PLANT_UNICYCLE = 1, CLR_PLANT_TORA = 2, CLR_PLANT_ACC = 3, CLR_PLANT_
 enum { CLR_ALG_TSIT5 = 0, CLR_ALG_RK4 = 1 };
 /* flags */
 enum {
-    CLR_FLAG_DEVICE_IO = 1,   /* every data pointer (inputs and outputs) is a DEVICE pointer; the call
-                                 only enqueues work on clr_stream(ctx) and does not synchronise */
+    CLR_FLAG_DEVICE_IO = 1,   /* the bulk data pointers (centers, radii, C, col_off, G, X, x0, Wd and every output
+                                 array incl. the hull) are DEVICE pointers: no host<->device copies are made and the
+                                 results are complete in stream order on clr_stream(ctx).  partition, clr_prepost and
+                                 clr_stats stay host pointers.  The DeepZ calls still synchronise once internally
+                                 (they read back how many cells need the large-cell pass). */
     CLR_FLAG_NO_STATS = 2     /* skip the per-layer statistics (stats may then be NULL) */
 };
 
