@@ -315,3 +315,25 @@ def test_zonotope_splitter_cells(ctx):
     ref = _oracle().deepz_zonotopes(_oracle().Net(net.as_tuples()), cells.C, cells.col_off, cells.G, post=("shift", -10.0))
     _cmp_boxes(got, ref)
     assert got["hull_lo"][0] == got["lo"].min() and got["hull_hi"][0] == got["hi"].max()
+
+
+@pytest.mark.parametrize("regime,count", [("mixed", 400), ("stable", 1500)])
+def test_results_do_not_depend_on_the_tiling(ctx, regime, count):
+    """The in-place layer products move columns while other warps still read neighbours: every tile size must give
+    bit-identical boxes (and the oracle's, within tolerance)."""
+    from clr_b200 import workloads
+    net = workloads.synthetic_relu_net()
+    dn = ctx.upload(net)
+    g = workloads.c4_grid(regime, last_dim_blocks=1)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii, cell_begin=777,
+                                  cell_count=count)
+    base = None
+    for T in (0, 1, 2, 3, 5, 8, 13, 21, 34):
+        ctx.set_tile_cells(T)
+        got = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=777, cell_count=count, stats=False)
+        if base is None:
+            base = got
+            _cmp_boxes(got, ref, atol=BOX_ATOL * max(1.0, np.abs(ref["hi"]).max()))
+        else:
+            assert np.array_equal(got["lo"], base["lo"]) and np.array_equal(got["hi"], base["hi"]), T
+    ctx.set_tile_cells(0)
