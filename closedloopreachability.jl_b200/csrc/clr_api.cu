@@ -842,12 +842,12 @@ int launch_rollout_blocked(clr_ctx* ctx, const PointNet& P, const RolloutArgs& A
     constexpr int NS = PlantDims<PLANT>::NS, NC = PlantDims<PLANT>::NC;
     const size_t slots = sizeof(double) * RO_R * (NS + NC) * 128;
     const size_t wbytes = sizeof(double) * (size_t)P.stotal;
-    if (slots + wbytes > (size_t)ctx->smem_optin / 4 - 1024) return launch_rollout_t<PLANT, CODE>(ctx, P, A);
+    if (slots + wbytes > (size_t)ctx->smem_optin / RO_MINBLK - 1024) return launch_rollout_t<PLANT, CODE>(ctx, P, A);
     const size_t smem = slots + wbytes;
     auto kern = rollout_blocked_kernel<PLANT, CODE>;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t span = 128 * RO_R;
-    int grid = (int)std::min<int64_t>((A.N + span - 1) / span, (int64_t)ctx->sms * 4);
+    int grid = (int)std::min<int64_t>((A.N + span - 1) / span, (int64_t)ctx->sms * RO_MINBLK);
     kern<<<grid, 128, smem, ctx->stream>>>(P, A, 1);
     CU(cudaGetLastError());
     ctx->launches++;

@@ -645,8 +645,11 @@ __device__ __forceinline__ void ro_mlp_small_blocked(const PointNet& net, const 
 // them at once (register blocked), then each one is integrated in turn; states and controls live in
 // thread-private shared-memory slots in between, so the ODE code exists once.
 #define RO_R 4
+#ifndef RO_MINBLK
+#define RO_MINBLK 4
+#endif
 template <int PLANT, int CODE>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, RO_MINBLK)
 rollout_blocked_kernel(PointNet net, RolloutArgs A, int in_smem) {
     constexpr int NS = PlantDims<PLANT>::NS, ND = PlantDims<PLANT>::ND, NC = PlantDims<PLANT>::NC;
     constexpr int NI = CODE >> 4, NO = CODE & 15;
