@@ -16,7 +16,7 @@ from .simulate import EnsembleSimulationSolution, SimulationSolution, sample_box
 
 def __getattr__(name):
     # the CUDA-backed parts are imported lazily so that pure-host helpers work before build()
-    if name in ("Context", "DeviceNetwork", "ClrError", "ClrArgumentError", "PrePostArg", "PLANTS"):
+    if name in ("Context", "DeviceNetwork", "CompiledPlant", "ClrError", "ClrArgumentError", "PrePostArg", "PLANTS"):
         from . import runtime
         return getattr(runtime, name)
     raise AttributeError(name)

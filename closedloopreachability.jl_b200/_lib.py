@@ -20,6 +20,7 @@ SYMBOLS = [
     "clr_set_profiling", "clr_last_pass_info",
     "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_zonotopes",
     "clr_deepz_fetch_zonotopes", "clr_forward_points", "clr_rollout",
+    "clr_plant_compile", "clr_plant_free", "clr_rollout_plant",
 ]
 
 
@@ -89,5 +90,12 @@ def lib():
     L.clr_rollout.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i32, vp, vp, dbl, dbl, dbl, i32, dbl, dbl,
                               i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32]
     L.clr_rollout.restype = i32
+    L.clr_plant_compile.argtypes = [vp, i32, i32, i32, C.c_char_p, C.POINTER(vp)]
+    L.clr_plant_compile.restype = i32
+    L.clr_plant_free.argtypes = [vp]
+    L.clr_plant_free.restype = None
+    L.clr_rollout_plant.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, dbl, dbl, dbl, i32, dbl, dbl, i32, i32, vp, vp, vp, vp, i32,
+                                    vp, vp, vp, i32]
+    L.clr_rollout_plant.restype = i32
     _lib = L
     return L

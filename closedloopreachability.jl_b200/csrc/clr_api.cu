@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <limits>
 #include <string>
 #include <vector>
@@ -17,6 +18,8 @@
 #include "rollout.cuh"
 
 namespace {
+
+const int kPlantCodes[5] = {66, 72, 136, 1, 2};   // evaluator codes of the rollout kernels (rollout.cuh: ro_eval)
 
 thread_local std::string g_create_error;
 
@@ -33,11 +36,9 @@ struct Compiled {            // one (network, pre/post-processing) pair on the d
     DevNet* dev = nullptr;
     PointNet pnet{};
     int ksreg = 8;
-    int warps = 8;
     int stored_width = 0;
     int point_code = 1;
     int inplace = 1;
-    int worst_cols_growth = 0;
 };
 
 }  // namespace
@@ -48,6 +49,15 @@ struct clr_net {
     std::vector<int> dims, act;
     std::vector<std::vector<double>> W, b;
     Compiled* compiled = nullptr;
+};
+
+// a run-time compiled plant right-hand side (NVRTC -> cubin -> cudaLibrary), one module per evaluator code, built on demand
+struct clr_plant {
+    clr_ctx* ctx = nullptr;
+    int ns = 0, nd = 0, nc = 0;
+    std::string source;             // prelude + rollout.cuh + the user's right-hand side
+    cudaLibrary_t lib[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaKernel_t kern[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct clr_ctx {
@@ -336,8 +346,6 @@ int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Com
     c->ksreg = 32;
     for (int o = 0; o < 4; o++) if (maxKsReg <= ks_opts[o]) { c->ksreg = ks_opts[o]; break; }
     c->inplace = maxRB <= DZ_THREADS / 32;   // every warp owns at most one row block
-    c->warps = maxRB >= 16 ? 16 : maxRB * (16 / maxRB);
-    if (c->warps < 4) c->warps = 4;
     {
         void* p = nullptr;
         cudaError_t e = cudaMalloc(&p, sizeof(DevNet));
@@ -854,6 +862,41 @@ int launch_rollout_blocked(clr_ctx* ctx, const PointNet& P, const RolloutArgs& A
     return 0;
 }
 
+// run-time compiled plant: same kernels, launched through the cudaLibrary handle of the plant
+int plant_build(clr_ctx* ctx, clr_plant* p, int slot, bool load);
+
+int launch_rollout_user(clr_ctx* ctx, const clr_plant* plant, int code, const PointNet& P, const RolloutArgs& A) {
+    int slot = 4;
+    for (int i = 0; i < 5; i++) if (kPlantCodes[i] == code) slot = i;
+    int brc = plant_build(ctx, const_cast<clr_plant*>(plant), slot, true);
+    if (brc) return brc;
+    const bool narrow = code > 2;
+    const size_t wbytes = sizeof(double) * (size_t)(narrow ? P.stotal : P.total_doubles);
+    size_t smem;
+    int in_smem = 1, grid;
+    if (narrow) {
+        const size_t slots = sizeof(double) * RO_R * (size_t)(plant->ns + plant->nc) * 128;
+        if (slots + wbytes > (size_t)ctx->smem_optin / RO_MINBLK - 1024)
+            return fail(ctx, CLR_ERR_ARG, "controller too large for the blocked rollout of a run-time compiled plant");
+        smem = slots + wbytes;
+        const int64_t span = 128 * RO_R;
+        grid = (int)std::min<int64_t>((A.N + span - 1) / span, (int64_t)ctx->sms * RO_MINBLK);
+    } else {
+        in_smem = wbytes <= (size_t)ctx->smem_optin - 1024;
+        smem = in_smem ? wbytes : 0;
+        const int per_sm = in_smem ? std::max(1, std::min(4, (int)((size_t)ctx->smem_optin / (smem + 1024)))) : 4;
+        grid = (int)std::min<int64_t>((A.N + 127) / 128, (int64_t)ctx->sms * per_sm);
+    }
+    void* fn = (void*)plant->kern[slot];
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PointNet Pc = P;
+    RolloutArgs Ac = A;
+    void* args[3] = {&Pc, &Ac, &in_smem};
+    CU(cudaLaunchKernel(fn, dim3(grid), dim3(128), args, smem, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
 template <int PLANT>
 int launch_rollout_p(clr_ctx* ctx, int code, const PointNet& P, const RolloutArgs& A) {
     switch (code) {
@@ -865,6 +908,134 @@ int launch_rollout_p(clr_ctx* ctx, int code, const PointNet& P, const RolloutArg
     }
 }
 }  // namespace
+
+extern "C" {
+
+}  // extern "C"
+
+// ---- run-time compiled plants (the reference's plant is an arbitrary user function) -------------------------
+namespace {
+
+const char* const kRolloutSource =
+#include "build/rollout_src.inc"
+    ;
+
+struct Nvrtc {
+    void* so = nullptr;
+    int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*DestroyProgram)(void**) = nullptr;
+    int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+    int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+    int (*GetProgramLog)(void*, char*) = nullptr;
+    int (*GetCUBINSize)(void*, size_t*) = nullptr;
+    int (*GetCUBIN)(void*, char*) = nullptr;
+    int (*AddNameExpression)(void*, const char*) = nullptr;
+    int (*GetLoweredName)(void*, const char*, const char**) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+Nvrtc& nvrtc() {
+    static Nvrtc n;
+    if (n.so) return n;
+    const char* cands[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+    for (const char* c : cands) { n.so = dlopen(c, RTLD_NOW | RTLD_LOCAL); if (n.so) break; }
+    if (!n.so) return n;
+#define CLR_SYM(field, name) *(void**)(&n.field) = dlsym(n.so, name)
+    CLR_SYM(CreateProgram, "nvrtcCreateProgram"); CLR_SYM(DestroyProgram, "nvrtcDestroyProgram");
+    CLR_SYM(CompileProgram, "nvrtcCompileProgram"); CLR_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    CLR_SYM(GetProgramLog, "nvrtcGetProgramLog"); CLR_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    CLR_SYM(GetCUBIN, "nvrtcGetCUBIN"); CLR_SYM(AddNameExpression, "nvrtcAddNameExpression");
+    CLR_SYM(GetLoweredName, "nvrtcGetLoweredName"); CLR_SYM(GetErrorString, "nvrtcGetErrorString");
+#undef CLR_SYM
+    n.ok = n.CreateProgram && n.DestroyProgram && n.CompileProgram && n.GetProgramLogSize && n.GetProgramLog &&
+           n.GetCUBINSize && n.GetCUBIN && n.AddNameExpression && n.GetLoweredName && n.GetErrorString;
+    return n;
+}
+
+// NVRTC-compile the plant's source for evaluator slot `slot` (kPlantCodes) and, with `load`, make the kernel launchable
+int plant_build(clr_ctx* ctx, clr_plant* p, int slot, bool load) {
+    if (p->kern[slot]) return 0;
+    Nvrtc& n = nvrtc();
+    if (!n.ok) return fail(ctx, CLR_ERR_STATE, "libnvrtc.so.12 could not be loaded: run-time compiled plants are unavailable");
+    void* prog = nullptr;
+    int rc = n.CreateProgram(&prog, p->source.c_str(), "clr_user_plant.cu", 0, nullptr, nullptr);
+    if (rc) return fail(ctx, CLR_ERR_STATE, "nvrtcCreateProgram: %s", n.GetErrorString(rc));
+    char expr[96];
+    snprintf(expr, sizeof(expr), kPlantCodes[slot] > 2 ? "rollout_blocked_kernel<1000, %d>" : "rollout_kernel<1000, %d>", kPlantCodes[slot]);
+    n.AddNameExpression(prog, expr);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo"};
+    rc = n.CompileProgram(prog, 4, opts);
+    if (rc) {
+        size_t ls = 0;
+        n.GetProgramLogSize(prog, &ls);
+        std::string log(ls ? ls : 1, '\0');
+        if (ls) n.GetProgramLog(prog, &log[0]);
+        n.DestroyProgram(&prog);
+        if (log.size() > 400) log = log.substr(log.size() - 400);   // the user's body is at the end of the source
+        return fail(ctx, CLR_ERR_ARG, "plant right-hand side does not compile: %s", log.c_str());
+    }
+    if (!load) { n.DestroyProgram(&prog); return 0; }
+    size_t cs = 0;
+    n.GetCUBINSize(prog, &cs);
+    std::vector<char> cubin(cs);
+    n.GetCUBIN(prog, cubin.data());
+    const char* low = nullptr;
+    std::string name = (n.GetLoweredName(prog, expr, &low) == 0 && low) ? low : "";
+    n.DestroyProgram(&prog);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaLibraryLoadData(&p->lib[slot], cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&p->kern[slot], p->lib[slot], name.c_str());
+    if (e != cudaSuccess) {
+        if (p->lib[slot]) { cudaLibraryUnload(p->lib[slot]); p->lib[slot] = nullptr; }
+        p->kern[slot] = nullptr;
+        return fail(ctx, CLR_ERR_CUDA, "loading the compiled plant failed: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t clr_plant_compile(clr_ctx* ctx, int32_t n_state, int32_t n_dist, int32_t n_ctrl, const char* rhs_body,
+                          clr_plant** out) {
+    if (!out || !rhs_body) return fail(ctx, CLR_ERR_ARG, "clr_plant_compile: NULL argument");
+    *out = nullptr;
+    if (n_state < 1 || n_state > 32 || n_dist < 0 || n_ctrl < 1 || n_dist + n_ctrl > 32)
+        return fail(ctx, CLR_ERR_DIM, "plant dimensions out of range (1..32 states, at most 32 disturbances + controls)");
+    char defs[640];
+    snprintf(defs, sizeof(defs),
+             "#define CLR_DEV_MAX_LAYERS %d\n"
+             "enum { CLR_ACT_ID = 0, CLR_ACT_RELU = 1, CLR_ACT_SIGMOID = 2, CLR_ACT_TANH = 3 };\n"
+             "enum { CLR_ALG_TSIT5 = 0, CLR_ALG_RK4 = 1 };\n"
+             "enum { CLR_PLANT_UNICYCLE = 1, CLR_PLANT_TORA = 2, CLR_PLANT_ACC = 3, CLR_PLANT_INVPEND = 4 };\n"
+             "#define CLR_ERR_CAPACITY (-2)\n"
+             "#define CLR_USER_NS %d\n#define CLR_USER_ND %d\n#define CLR_USER_NC %d\n"
+             "__device__ void clr_user_rhs(const double* x, const double* q, double* dx);\n",
+             CLR_DEV_MAX_LAYERS, n_state, n_dist, n_ctrl);
+    clr_plant* p = new clr_plant();
+    p->ctx = ctx; p->ns = n_state; p->nd = n_dist; p->nc = n_ctrl;
+    p->source = defs;
+    p->source += kRolloutSource;
+    p->source += "\n__device__ void clr_user_rhs(const double* x, const double* q, double* dx) {\n";
+    p->source += rhs_body;
+    p->source += "\n}\n";
+    // compile one evaluator now: the caller learns about errors in the right-hand side here, not at the first rollout
+    int rc = plant_build(ctx, p, 3 /* code 1: generic evaluator */, ctx != nullptr);
+    if (rc) { delete p; return rc; }
+    *out = p;
+    return 0;
+}
+
+void clr_plant_free(clr_plant* p) {
+    if (!p) return;
+    if (p->ctx) cudaSetDevice(p->ctx->device);
+    for (int i = 0; i < 5; i++) if (p->lib[i]) cudaLibraryUnload(p->lib[i]);
+    delete p;
+}
+
+}  // extern "C"
 
 extern "C" {
 
@@ -897,7 +1068,7 @@ int32_t clr_forward_points(clr_ctx* ctx, const clr_net* net_c, const clr_prepost
     return 0;
 }
 
-int32_t clr_rollout(clr_ctx* ctx, const clr_net* net_c, const clr_prepost* pp, int32_t plant,
+static int32_t rollout_impl(clr_ctx* ctx, const clr_net* net_c, const clr_prepost* pp, int32_t plant, const clr_plant* user,
                     int32_t n_state, int32_t n_dist, int32_t n_ctrl, int64_t N, int32_t iters,
                     const double* x0, const double* Wd, double t0, double tau, double T, int32_t alg,
                     double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end,
@@ -907,13 +1078,15 @@ int32_t clr_rollout(clr_ctx* ctx, const clr_net* net_c, const clr_prepost* pp, i
     clr_net* net = const_cast<clr_net*>(net_c);
     if (!net || N < 0 || iters < 0) return fail(ctx, CLR_ERR_ARG, "clr_rollout: bad argument");
     int ns, nd, nc;
-    switch (plant) {
+    if (user) { ns = user->ns; nd = user->nd; nc = user->nc; plant = CLR_PLANT_UNICYCLE; }
+    else switch (plant) {
         case CLR_PLANT_UNICYCLE: ns = 4; nd = 1; nc = 2; break;
         case CLR_PLANT_TORA: ns = 4; nd = 0; nc = 1; break;
         case CLR_PLANT_ACC: ns = 6; nd = 0; nc = 1; break;
         case CLR_PLANT_INVPEND: ns = 2; nd = 0; nc = 1; break;
         default: return fail(ctx, CLR_ERR_ARG, "unknown plant id %d", plant);
     }
+    if (user && user->ctx != ctx) return fail(ctx, CLR_ERR_STATE, "the plant was compiled for another context (or without one: syntax check only)");
     if (n_state != ns || n_dist != nd || n_ctrl != nc)
         return fail(ctx, CLR_ERR_DIM, "plant %d has %d states, %d disturbances, %d controls; got %d, %d, %d", plant, ns, nd, nc, n_state, n_dist, n_ctrl);
     if (alg != CLR_ALG_TSIT5 && alg != CLR_ALG_RK4) return fail(ctx, CLR_ERR_ARG, "unknown ODE algorithm %d", alg);
@@ -959,7 +1132,8 @@ int32_t clr_rollout(clr_ctx* ctx, const clr_net* net_c, const clr_prepost* pp, i
         A.nreject = nreject ? (int*)(base + oR) : nullptr;
         if (log_cap > 0) { A.log_n = (int*)(base + oLn); A.log_t = (double*)(base + oLt); A.log_u = (double*)(base + oLu); }
     }
-    switch (plant) {
+    if (user) rc = launch_rollout_user(ctx, user, c->point_code, c->pnet, A);
+    else switch (plant) {
         case CLR_PLANT_UNICYCLE: rc = launch_rollout_p<CLR_PLANT_UNICYCLE>(ctx, c->point_code, c->pnet, A); break;
         case CLR_PLANT_TORA: rc = launch_rollout_p<CLR_PLANT_TORA>(ctx, c->point_code, c->pnet, A); break;
         case CLR_PLANT_ACC: rc = launch_rollout_p<CLR_PLANT_ACC>(ctx, c->point_code, c->pnet, A); break;
@@ -982,6 +1156,28 @@ int32_t clr_rollout(clr_ctx* ctx, const clr_net* net_c, const clr_prepost* pp, i
         if (err) return fail(ctx, err, "step log overflow: a period took more than log_cap - 1 = %d accepted steps", log_cap - 1);
     }
     return 0;
+}
+
+
+int32_t clr_rollout(clr_ctx* ctx, const clr_net* net, const clr_prepost* pp, int32_t plant,
+                    int32_t n_state, int32_t n_dist, int32_t n_ctrl, int64_t N, int32_t iters,
+                    const double* x0, const double* Wd, double t0, double tau, double T, int32_t alg,
+                    double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end,
+                    double* U, int32_t* naccept, int32_t* nreject, int32_t log_cap, int32_t* log_n,
+                    double* log_t, double* log_u, int32_t flags) {
+    return rollout_impl(ctx, net, pp, plant, nullptr, n_state, n_dist, n_ctrl, N, iters, x0, Wd, t0, tau, T, alg, abstol, reltol,
+                        substeps, pow_mode, X_end, U, naccept, nreject, log_cap, log_n, log_t, log_u, flags);
+}
+
+int32_t clr_rollout_plant(clr_ctx* ctx, const clr_net* net, const clr_prepost* pp, const clr_plant* plant, int64_t N,
+                          int32_t iters, const double* x0, const double* Wd, double t0, double tau, double T, int32_t alg,
+                          double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end, double* U,
+                          int32_t* naccept, int32_t* nreject, int32_t log_cap, int32_t* log_n, double* log_t,
+                          double* log_u, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (!plant) return fail(ctx, CLR_ERR_ARG, "clr_rollout_plant: NULL plant");
+    return rollout_impl(ctx, net, pp, 0, plant, plant->ns, plant->nd, plant->nc, N, iters, x0, Wd, t0, tau, T, alg, abstol,
+                        reltol, substeps, pow_mode, X_end, U, naccept, nreject, log_cap, log_n, log_t, log_u, flags);
 }
 
 }  // extern "C"

@@ -23,8 +23,8 @@ struct DevLayer {
     int m;            // output rows (M)
     int ksteps;       // ceil(n / 4): DMMA k-steps
     int rblocks;      // ceil(m / 8): DMMA row blocks
-    int pitch_in;     // column pitch (doubles) of the input store
-    int pitch_out;    // column pitch of the output store (= next layer's pitch_in)
+    int pitch_in;     // column pitch (doubles) of the stores: DevNet::max_pitch for every layer (one pitch per network)
+    int pitch_out;
     int act;          // CLR_ACT_*
     int collapse;     // 1: LazySets' one-row linear_map (single generator sum_j |W g_j|)
     int net_layer;    // index into clr_stats arrays, -1 for folded pre/post layers
@@ -40,8 +40,7 @@ struct DevNet {
     int m_out;        // rows of the output sets
     int max_rows;     // max over layers of m and n_in
     int max_pitch;    // max over all stores
-    int max_growth;   // sum over layers of appended generators in the worst case
-    int pad_[2];
+    int pad_[3];
     DevLayer layer[CLR_DEV_MAX_LAYERS];
 };
 

@@ -8,7 +8,10 @@
 // weights are staged once per CTA in shared memory and read as warp-wide broadcasts, and the only
 // HBM traffic is the state/disturbance read and the X_end / U write per period.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include "common.cuh"
+#endif
+// (under NVRTC -- user-supplied plants, clr_plant_compile -- the host prepends the few constants this file needs)
 
 #define RO_MAX_LAYERS (CLR_DEV_MAX_LAYERS)
 
@@ -259,9 +262,19 @@ template <> struct PlantDims<CLR_PLANT_TORA> { static constexpr int NS = 4, ND =
 template <> struct PlantDims<CLR_PLANT_ACC> { static constexpr int NS = 6, ND = 0, NC = 1; };
 template <> struct PlantDims<CLR_PLANT_INVPEND> { static constexpr int NS = 2, ND = 0, NC = 1; };
 
+#ifdef CLR_USER_NS
+// run-time compiled plant (clr_plant_compile): dimensions and right-hand side body come from the caller
+#define CLR_PLANT_USER 1000
+template <> struct PlantDims<CLR_PLANT_USER> { static constexpr int NS = CLR_USER_NS, ND = CLR_USER_ND, NC = CLR_USER_NC; };
+__device__ void clr_user_rhs(const double* x, const double* q, double* dx);   // defined by the host after this source
+#endif
+
 // x: NS dynamic states, q: the constant tail [w; u]
 template <int PLANT>
 __device__ __forceinline__ void plant_rhs(const double* x, const double* q, double* dx) {
+#ifdef CLR_USER_NS
+    if (PLANT == CLR_PLANT_USER) { clr_user_rhs(x, q, dx); return; }
+#endif
     if (PLANT == CLR_PLANT_UNICYCLE) {            // models/Unicycle/Unicycle.jl:36-47
         double sn, cs;
         sincos(x[2], &sn, &cs);
@@ -540,9 +553,10 @@ rollout_kernel(PointNet net, RolloutArgs A, int in_smem) {
         for (int i = 0; i < NS; i++) x[i] = A.x0[j * NS + i];
         double t = A.t0;
         for (int it = 0; it < A.iters; it++) {
-            double xin[8], u[8];
+            constexpr int NX = NS > 8 ? NS : 8, NU = NC > 8 ? NC : 8;
+            double xin[NX], u[NU];
 #pragma unroll
-            for (int i = 0; i < 8; i++) xin[i] = i < NS ? x[i] : 0.0;
+            for (int i = 0; i < NX; i++) xin[i] = i < NS ? x[i] : 0.0;
             ro_eval<CODE>(net, w, xin, u);
             const long long cell = (long long)it * A.N + j;
 #pragma unroll

@@ -123,6 +123,30 @@ class DeviceNetwork:
         self.h = None
 
 
+class CompiledPlant:
+    """A plant right-hand side compiled at run time (clr_plant_compile): ``rhs_body`` is the CUDA C body of
+    ``rhs(const double* x, const double* q, double* dx)`` with x the dynamic states and q = [w; u].
+    ``ctx=None`` only checks that the source compiles (no device needed)."""
+
+    def __init__(self, ctx, n_state: int, n_dist: int, n_ctrl: int, rhs_body: str):
+        self.ctx = ctx
+        self.dims = (int(n_state), int(n_dist), int(n_ctrl))
+        L = ctx.L if ctx is not None else _lib.lib()
+        h = C.c_void_p()
+        rc = L.clr_plant_compile(ctx.h if ctx is not None else None, n_state, n_dist, n_ctrl, rhs_body.encode(), C.byref(h))
+        if rc != 0:
+            _raise(rc, (L.clr_last_error(ctx.h if ctx is not None else None) or b"").decode())
+        self.L, self.h = L, h
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.clr_plant_free(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+
 class Context:
     """clr_ctx: bound to one CUDA device; owns a stream and all device scratch memory."""
 
@@ -176,6 +200,9 @@ class Context:
 
     def upload(self, net: FeedforwardNetwork) -> DeviceNetwork:
         return DeviceNetwork(self, net)
+
+    def compile_plant(self, n_state: int, n_dist: int, n_ctrl: int, rhs_body: str) -> CompiledPlant:
+        return CompiledPlant(self, n_state, n_dist, n_ctrl, rhs_body)
 
     # ---- DeepZ ------------------------------------------------------------------------------------
     def deepz_boxgrid(self, dnet: DeviceNetwork, partition, centers, radii, cell_begin=0, cell_count=None,
@@ -287,13 +314,18 @@ class Context:
     def rollout(self, dnet: DeviceNetwork, plant, x0, Wd, t0, tau, T, iters, alg="Tsit5", abstol=1e-6, reltol=1e-3,
                 substeps=4, pow_mode=1, pre=None, post=None, log_cap=0, counts=True):
         """x0: (N, n_state); Wd: (iters, N, n_dist) or None.  Returns X_end (iters, N, n_state), U (iters, N, n_ctrl)."""
-        pid = PLANTS[plant] if isinstance(plant, str) else int(plant)
-        ns, nd, nc = PLANT_DIMS.get(pid, (0, 0, 0))
+        user = plant if isinstance(plant, CompiledPlant) else None
+        pid = 0 if user else (PLANTS[plant] if isinstance(plant, str) else int(plant))
+        ns, nd, nc = user.dims if user else PLANT_DIMS.get(pid, (0, 0, 0))
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         if x0.ndim != 2:
             raise ClrArgumentError(ERR_DIM, "x0 must be (N, n_state)")
         N = x0.shape[0]
+        if user and x0.shape[1] != ns:
+            raise ClrArgumentError(ERR_DIM, f"the plant has {ns} states, x0 has {x0.shape[1]} columns")
         if nd:
+            if Wd is None:
+                raise ClrArgumentError(ERR_ARG, "the plant has disturbances: Wd is required")
             Wd = np.ascontiguousarray(Wd, dtype=np.float64).reshape(iters, N, nd)
         pp = PrePostArg(pre, post)
         X_end = np.empty((iters, N, ns))
@@ -305,11 +337,14 @@ class Context:
             ln = np.zeros((iters, N), dtype=np.int32)
             lt = np.zeros((iters, N, log_cap))
             lu = np.zeros((iters, N, log_cap, ns + nd + nc))
-        rc = self.L.clr_rollout(self.h, dnet.h, C.byref(pp.s), pid, x0.shape[1], nd, nc, N, int(iters), _ptr(x0),
-                                _ptr(Wd) if nd else None, float(t0), float(tau), float(T),
-                                0 if alg == "Tsit5" else 1, float(abstol), float(reltol), int(substeps),
-                                int(pow_mode), _ptr(X_end), _ptr(U), _ptr(na), _ptr(nr), int(log_cap), _ptr(ln),
-                                _ptr(lt), _ptr(lu), 0)
+        tail = (float(t0), float(tau), float(T), 0 if alg == "Tsit5" else 1, float(abstol), float(reltol), int(substeps),
+                int(pow_mode), _ptr(X_end), _ptr(U), _ptr(na), _ptr(nr), int(log_cap), _ptr(ln), _ptr(lt), _ptr(lu), 0)
+        if user:
+            rc = self.L.clr_rollout_plant(self.h, dnet.h, C.byref(pp.s), user.h, N, int(iters), _ptr(x0),
+                                          _ptr(Wd) if nd else None, *tail)
+        else:
+            rc = self.L.clr_rollout(self.h, dnet.h, C.byref(pp.s), pid, x0.shape[1], nd, nc, N, int(iters), _ptr(x0),
+                                    _ptr(Wd) if nd else None, *tail)
         self._check(rc)
         out = {"X_end": X_end, "U": U}
         if counts:

@@ -69,6 +69,7 @@ enum {
 
 typedef struct clr_ctx clr_ctx;
 typedef struct clr_net clr_net;
+typedef struct clr_plant clr_plant;
 
 /* Pre/post-processing of controller_forward (src/solve.jl:211, :213).  Always HOST pointers. */
 typedef struct {
@@ -179,6 +180,24 @@ int32_t clr_rollout(clr_ctx* ctx, const clr_net* net, const clr_prepost* pp, int
                     double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end,
                     double* U, int32_t* naccept, int32_t* nreject, int32_t log_cap, int32_t* log_n,
                     double* log_t, double* log_u, int32_t flags);
+
+/* ---- run-time compiled plants ------------------------------------------------------------------- */
+/*
+ * The reference's plant is an arbitrary user function f!(dx, x, p, t) on the extended state
+ * (RA.inplace_field!(ivp), ext/ClosedLoopReachabilityOrdinaryDiffEqExt.jl:33-37).  clr_plant_compile takes the BODY of
+ *     __device__ void rhs(const double* x, const double* q, double* dx)
+ * in CUDA C (x: the n_state dynamic states, q: the constant tail [w (n_dist); u (n_ctrl)], dx: n_state derivatives),
+ * compiles the rollout kernels around it with NVRTC for sm_100a and returns a handle for clr_rollout_plant, which
+ * otherwise behaves exactly like clr_rollout.  ctx == NULL compiles only (syntax check, no device needed).
+ */
+int32_t clr_plant_compile(clr_ctx* ctx, int32_t n_state, int32_t n_dist, int32_t n_ctrl, const char* rhs_body,
+                          clr_plant** out);
+void clr_plant_free(clr_plant* plant);
+int32_t clr_rollout_plant(clr_ctx* ctx, const clr_net* net, const clr_prepost* pp, const clr_plant* plant, int64_t N,
+                          int32_t iters, const double* x0, const double* Wd, double t0, double tau, double T, int32_t alg,
+                          double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end, double* U,
+                          int32_t* naccept, int32_t* nreject, int32_t log_cap, int32_t* log_n, double* log_t,
+                          double* log_u, int32_t flags);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 MAX_LAYERS = 32
 ACT_IDS = {"Id": 0, "ReLU": 1, "Sigmoid": 2, "Tanh": 3}
-PLANTS = {"Unicycle": 1, "TORA": 2, "ACC": 3, "InvertedPendulum": 4}
+PLANTS = {"Unicycle": 1, "TORA": 2, "ACC": 3, "InvertedPendulum": 4, "AttitudeControl": 5}
 
 
 class Stats(C.Structure):

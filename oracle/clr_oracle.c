@@ -449,7 +449,7 @@ int clro_forward_points(const clro_net* net, const clro_prepost* pp, int nx, int
 }
 
 /* ---- plants (extended state [x; w; u], models/<name>/<name>.jl) ------------------------------- */
-enum { PLANT_UNICYCLE = 1, PLANT_TORA = 2, PLANT_ACC = 3, PLANT_INVPEND = 4 };
+enum { PLANT_UNICYCLE = 1, PLANT_TORA = 2, PLANT_ACC = 3, PLANT_INVPEND = 4, PLANT_ATTITUDE = 5 };
 
 static void plant_rhs(int plant, const double* x, double* dx, int n_ext) {
     for (int i = 0; i < n_ext; i++) dx[i] = 0.0;
@@ -478,6 +478,16 @@ static void plant_rhs(int plant, const double* x, double* dx, int n_ext) {
             dx[0] = x[1];
             dx[1] = 2.0 * sin(x[0]) + 8.0 * (x[2] - 0.0 * x[1]);
             break;
+        case PLANT_ATTITUDE: { /* models/AttitudeControl/AttitudeControl.jl:34-57 */
+            double xi = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
+            dx[0] = 0.25 * (x[6] + x[1] * x[2]);
+            dx[1] = 0.5 * (x[7] - 3 * x[0] * x[2]);
+            dx[2] = x[8] + 2 * x[0] * x[1];
+            dx[3] = 0.5 * (x[1] * (xi - x[5]) + x[2] * (xi + x[4]) + x[0] * (xi + 1));
+            dx[4] = 0.5 * (x[0] * (xi + x[5]) + x[2] * (xi - x[3]) + x[1] * (xi + 1));
+            dx[5] = 0.5 * (x[0] * (xi - x[4]) + x[1] * (xi + x[3]) + x[2] * (xi + 1));
+            break;
+        }
         default: break;
     }
 }

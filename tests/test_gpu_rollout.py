@@ -134,3 +134,49 @@ def test_simulate_mirror(ctx):
     np.testing.assert_allclose(u_last[-1, :4], sol.X_end[-1, 3], rtol=0, atol=1e-15)
     with pytest.raises(ValueError):
         clr_b200.simulate(ctx, prob, trajectories=4)
+
+
+UNICYCLE_RHS = """
+    double sn, cs;
+    sincos(x[2], &sn, &cs);
+    dx[0] = x[3] * cs;
+    dx[1] = x[3] * sn;
+    dx[2] = q[2];
+    dx[3] = q[1] + q[0];
+"""
+ATTITUDE_RHS = """
+    const double xi = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
+    dx[0] = 0.25 * (q[0] + x[1] * x[2]);
+    dx[1] = 0.5 * (q[1] - 3 * x[0] * x[2]);
+    dx[2] = q[2] + 2 * x[0] * x[1];
+    dx[3] = 0.5 * (x[1] * (xi - x[5]) + x[2] * (xi + x[4]) + x[0] * (xi + 1));
+    dx[4] = 0.5 * (x[0] * (xi + x[5]) + x[2] * (xi - x[3]) + x[1] * (xi + 1));
+    dx[5] = 0.5 * (x[0] * (xi - x[4]) + x[1] * (xi + x[3]) + x[2] * (xi + 1));
+"""
+
+
+def test_runtime_compiled_plants(ctx):
+    """clr_plant_compile / clr_rollout_plant: a user right-hand side compiled with NVRTC.  The Unicycle source must
+    reproduce the built-in plant bit for bit; AttitudeControl (models/AttitudeControl/AttitudeControl.jl:34-57, a plant
+    that is not built in) is checked against the oracle."""
+    from clr_b200 import runtime, workloads
+    uni = load_net("Unicycle")
+    du = ctx.upload(uni)
+    x0, Wd = workloads.unicycle_samples(np.random.default_rng(21), 3000, 10)
+    plant = ctx.compile_plant(4, 1, 2, UNICYCLE_RHS)
+    a = ctx.rollout(du, "Unicycle", x0, Wd, 0.0, 0.2, 2.0, 10, post=("shift", -20.0))
+    b = ctx.rollout(du, plant, x0, Wd, 0.0, 0.2, 2.0, 10, post=("shift", -20.0))
+    assert np.array_equal(a["X_end"], b["X_end"]) and np.array_equal(a["U"], b["U"]) and np.array_equal(a["naccept"], b["naccept"])
+    att = load_net("AttitudeControl")
+    da = ctx.upload(att)
+    lo = np.array([-0.45, -0.55, 0.65, -0.75, 0.85, -0.65])          # AttitudeControl.jl:72-73
+    hi = np.array([-0.44, -0.54, 0.66, -0.74, 0.86, -0.64])
+    xa = np.random.default_rng(22).uniform(lo, hi, (1500, 6))
+    pa = ctx.compile_plant(6, 0, 3, ATTITUDE_RHS)
+    got = ctx.rollout(da, pa, xa, None, 0.0, 0.1, 3.0, 30)
+    ref = _oracle().rollout(_oracle().Net(att.as_tuples()), "AttitudeControl", 6, 0, 3, xa, None, 0.0, 0.1, 3.0, 30)
+    assert np.array_equal(got["naccept"], ref["naccept"])
+    np.testing.assert_allclose(got["X_end"], ref["X_end"], rtol=0, atol=TRAJ_ATOL)
+    np.testing.assert_allclose(got["U"], ref["U"], rtol=0, atol=TRAJ_ATOL)
+    with pytest.raises(runtime.ClrArgumentError):
+        ctx.rollout(da, plant, xa, None, 0.0, 0.1, 3.0, 30)          # 6 state columns into a 4-state plant

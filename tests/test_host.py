@@ -214,3 +214,15 @@ def test_controlled_plant_and_processing_mirror():
         clr_b200.ControlledPlant("Unicycle", lo[:6], hi[:6], net, vars_, 0.2)
     x = clr_b200.sample_box(np.random.default_rng(0), lo[:4], hi[:4], 5, include_vertices=True)
     assert x.shape == (5 + 16, 4) and np.all(x >= np.array(lo[:4])) and np.all(x <= np.array(hi[:4]))
+
+
+def test_runtime_plant_source_compiles_without_a_device():
+    """clr_plant_compile with ctx == NULL: NVRTC syntax check of a user right-hand side (no GPU needed)."""
+    from clr_b200 import runtime
+    ok = "dx[0] = x[1]; dx[1] = 2.0 * sin(x[0]) + 8.0 * q[0];"          # models/InvertedPendulum/InvertedPendulum.jl:44-51
+    runtime.CompiledPlant(None, 2, 0, 1, ok)
+    with pytest.raises(runtime.ClrArgumentError) as e:
+        runtime.CompiledPlant(None, 2, 0, 1, "dx[0] = no_such_symbol;")
+    assert "no_such_symbol" in str(e.value)
+    with pytest.raises(runtime.ClrArgumentError):
+        runtime.CompiledPlant(None, 0, 0, 1, ok)
