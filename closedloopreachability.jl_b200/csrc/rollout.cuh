@@ -615,7 +615,7 @@ __device__ __forceinline__ void ro_mlp_small_blocked(const PointNet& net, const 
 #pragma unroll
                     for (int k = 0; k < NI / 2; k++) { s = fma(wv[k].x, va[r][2 * k], s); s = fma(wv[k].y, va[r][2 * k + 1], s); }
                     s += b1;
-                    const double h = relu ? fmax(s, 0.0) : ro_act(a1, s);
+                    const double h = relu ? 0.5 * (s + fabs(s)) : ro_act(a1, s);   // exact max(s, 0) in two FP64 instructions
 #pragma unroll
                     for (int o = 0; o < NO / 2; o++) { vb[r][2 * o] = fma(vv[o].x, h, vb[r][2 * o]); vb[r][2 * o + 1] = fma(vv[o].y, h, vb[r][2 * o + 1]); }
                 }

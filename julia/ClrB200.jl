@@ -127,4 +127,16 @@ function rollout(ctx::Context, dnet::DeviceNetwork, pp::PrePost, plant::Integer,
     return Xend, U
 end
 
+"""
+A plant that is not built in: `rhs_body` is the CUDA C body of `rhs(const double* x, const double* q, double* dx)` (x: the
+dynamic states, q = [w; u]) -- the device-side twin of the user's `f!(dx, x, p, t)` (RA.inplace_field!(ivp),
+ext/ClosedLoopReachabilityOrdinaryDiffEqExt.jl:33-37).  Returns the handle `clr_rollout_plant` takes in place of the plant id.
+"""
+function compile_plant(ctx::Context, n_state::Integer, n_dist::Integer, n_ctrl::Integer, rhs_body::AbstractString)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:clr_plant_compile, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Cstring, Ref{Ptr{Cvoid}}),
+                     ctx.h, n_state, n_dist, n_ctrl, rhs_body, out))
+    return out[]
+end
+
 end # module
