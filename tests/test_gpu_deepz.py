@@ -337,3 +337,43 @@ def test_results_do_not_depend_on_the_tiling(ctx, regime, count):
         else:
             assert np.array_equal(got["lo"], base["lo"]) and np.array_equal(got["hi"], base["hi"]), T
     ctx.set_tile_cells(0)
+
+
+def test_device_resident_io_and_two_contexts(ctx):
+    """CLR_FLAG_DEVICE_IO: inputs and outputs as device pointers (torch CUDA tensors), for zonotope batches and box
+    grids, on a second context of the same device; results equal the host-buffer path bit for bit."""
+    import torch
+    import clr_b200
+    from clr_b200 import _lib, runtime, workloads
+    net = load_net("TORA_ReLU")
+    rng = np.random.default_rng(31)
+    C, off, G = workloads.random_zonotopes(rng, 500, 4, 0, 12, -0.6, 0.6, 0.02)
+    host = ctx.deepz_zonotopes(ctx.upload(net), C, off, G, post=("shift", -10.0), hull=True)
+    ctx2 = runtime.Context(0)
+    try:
+        dn2 = ctx2.upload(net)
+        dev = torch.device("cuda", 0)
+        dC, dO, dG = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (C, off, G))
+        lo = torch.empty((500, 1), dtype=torch.float64, device=dev)
+        hi = torch.empty_like(lo)
+        hl = torch.empty(1, dtype=torch.float64, device=dev)
+        hh = torch.empty_like(hl)
+        pp = runtime.PrePostArg(None, ("shift", -10.0))
+        st = _lib.Stats()
+        ctx2.deepz_zonotopes_dev(dn2, 4, 500, dC, dO, dG, pp, lo, hi, hl, hh, stats=st)
+        ctx2.synchronize()
+        assert np.array_equal(lo.cpu().numpy(), host["lo"]) and np.array_equal(hi.cpu().numpy(), host["hi"])
+        assert hl.item() == host["hull_lo"][0] and hh.item() == host["hull_hi"][0]
+        assert list(st.sum_p_in)[:4] == host["stats"]["sum_p_in"]
+        g = clr_b200.split_box(TORA_LO, TORA_HI, [4, 4, 3, 5])
+        cc = torch.from_numpy(np.concatenate(g.centers)).to(dev)
+        rr = torch.from_numpy(np.concatenate(g.radii)).to(dev)
+        lo2 = torch.empty((240, 1), dtype=torch.float64, device=dev)
+        hi2 = torch.empty_like(lo2)
+        ctx2.deepz_boxgrid_dev(dn2, 4, g.partition, cc, rr, 0, 240, pp, lo2, hi2)
+        ctx2.synchronize()
+        ref = ctx.deepz_boxgrid(ctx.upload(net), g.partition, g.centers, g.radii, post=("shift", -10.0))
+        assert np.array_equal(lo2.cpu().numpy(), ref["lo"]) and np.array_equal(hi2.cpu().numpy(), ref["hi"])
+        assert ctx2.launch_count > 0 and ctx2.stream != ctx.stream
+    finally:
+        ctx2.close()
