@@ -26,3 +26,16 @@ C += np.array([90.0, 32.0, 0.0, 10.0, 30.0, 0.0])
 us = bench(lambda: ctx.deepz_zonotopes(da, C, off, G, pre=(A, d), stats=False))
 print(f"C1 ACC single zonotope (n = 6, p = 14): {us:.1f} us/propagation")
 ctx.close()
+
+# C3: Quadrotor controller (12 -> 64^3 -> 3, sigmoid), 4^6 = 4096 cells of X0 (models/Quadrotor/Quadrotor.jl:98-99)
+ctx = runtime.Context(0)
+quad = clr_b200.FeedforwardNetwork.load_npz(os.path.join(gold, "Quadrotor.npz"))
+dq = ctx.upload(quad)
+r = 0.01 * np.array([0.4] * 6 + [0.0] * 6)
+gq = clr_b200.split_box(-r, r, [4] * 6 + [1] * 6)
+out = ctx.deepz_boxgrid(dq, gq.partition, gq.centers, gq.radii)
+us = bench(lambda: ctx.deepz_boxgrid(dq, gq.partition, gq.centers, gq.radii, stats=False), reps=50)
+fl = out["stats"]["flops"]
+print(f"C3 Quadrotor 4096 cells per call: {us:.1f} us/call = {4096/us:.2f} M propagations/s, {fl/us/1e6:.2f} algorithmic TFLOP/s, "
+      f"p_in/cell {[x/4096 for x in out['stats']['sum_p_in']]}")
+ctx.close()
