@@ -175,6 +175,39 @@ __global__ void k_wreg16_smem(double* out, int iters, const double* __restrict__
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+
+// ---- do DMMA and DFMA share a pipe?  warps 0..7 of a CTA run DMMA chains, warps 8..15 DFMA chains (mode bit 0 / bit 1)
+__global__ void k_mixed(double* out, int iters_mma, int iters_fma, int mode, double a0, double b0) {
+    const int warp = threadIdx.x >> 5;
+    double s = 0;
+    if (warp < 8) {
+        if (!(mode & 1)) return;
+        double d[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { d[c][0] = threadIdx.x; d[c][1] = c; }
+        double a = a0 + threadIdx.x * 1e-9, b = b0;
+        for (int i = 0; i < iters_mma; i++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) dmma884(d[c][0], d[c][1], a, b);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) s += d[c][0] + d[c][1];
+    } else {
+        if (!(mode & 2)) return;
+        double d[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) d[c] = threadIdx.x + c;
+        double a = a0 + threadIdx.x * 1e-9, b = b0;
+        for (int i = 0; i < iters_fma; i++) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) d[c] = fma(d[c], a, b);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) s += d[c];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 float timeit(F f, int reps = 3) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -208,6 +241,15 @@ int main() {
         RUN("dmma1688", k_dmma1688, 1, 2048); RUN("dmma1688", k_dmma1688, 4, 2048);
         RUN("dmma16816", k_dmma16816, 1, 4096); RUN("dmma16816", k_dmma16816, 4, 4096);
         RUN("dfma", k_dfma, 1, 64); RUN("dfma", k_dfma, 4, 64); RUN("dfma", k_dfma, 8, 64);
+    }
+    // DMMA and DFMA warps side by side: separate pipes (time = max) or a shared one (time = sum)?
+    {
+        const int im = 4096, ifm = 4096 * 4;   // 8 warps x 4096 x 4 DMMA (512 flop) vs 8 warps x 16384 x 8 DFMA (64 flop): equal flops
+        for (int mode = 1; mode <= 3; mode++) {
+            float ms = timeit([&] { k_mixed<<<sms, 512>>>(out, im, ifm, mode, 1.0000001, 1e-9); });
+            double fl = (double)sms * 8 * ((mode & 1 ? (double)im * 4 * 512 : 0) + (mode & 2 ? (double)ifm * 8 * 64 : 0));
+            printf("mixed mode %d (1 = DMMA warps, 2 = DFMA warps, 3 = both): %8.3f ms %7.2f TFLOP/s\n", mode, ms, fl / ms / 1e9);
+        }
     }
     // W-in-registers + B from smem
     {
