@@ -668,13 +668,36 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         if (STATS && warp == 0 && Ly.net_layer >= 0) S.cellUnst[ci][Ly.net_layer] = (unsigned short)u;
                     }
                 }
-                dz_layout(w[0], w[1], nCells, capCols, lane, off0, off1, keep, total);
+                // one scan for both the column offsets (low 16 bits) and the item offsets (high 16 bits)
+                int ub0, ub1, nIt;
+                {
+                    int s0 = w[0] | (uu[0] << 16), s1 = w[1] | (uu[1] << 16);
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const int t0 = __shfl_up_sync(0xffffffffu, s0, dd);
+                        const int t1 = __shfl_up_sync(0xffffffffu, s1, dd);
+                        if (lane >= dd) { s0 += t0; s1 += t1; }
+                    }
+                    s1 += __shfl_sync(0xffffffffu, s0, 31);
+                    const int e0 = s0 & 0xFFFF, e1 = s1 & 0xFFFF;                     // inclusive column ends
+                    const bool f0 = lane < nCells && e0 + 8 <= capCols;
+                    const bool f1 = lane + 32 < nCells && e1 + 8 <= capCols;
+                    keep = __popc(__ballot_sync(0xffffffffu, f0)) + __popc(__ballot_sync(0xffffffffu, f1));
+                    off0 = e0 - w[0]; off1 = e1 - w[1];
+                    ub0 = (s0 >> 16) - uu[0]; ub1 = (s1 >> 16) - uu[1];               // first item of cells lane, lane + 32
+                    const int l0 = __shfl_sync(0xffffffffu, s0, (keep - 1) & 31);
+                    const int l1 = __shfl_sync(0xffffffffu, s1, (keep - 33) & 31);
+                    const int last = keep == 0 ? 0 : (keep <= 32 ? l0 : l1);
+                    total = last & 0xFFFF;
+                    nIt = last >> 16;                                                 // generators appended in the kept cells
+                }
                 int* cn = S.colOff[flip];                // the layout the data just left is free: it becomes the next one
                 if (warp == 0) {
                     if (lane < keep) cn[lane] = off0;
                     if (lane + 32 < keep) cn[lane + 32] = off1;
                     if (lane == 0) {
                         cn[keep] = total;
+                        S.nItems = nIt;
                         if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
                         if (keep > 0) S.peakNeed = fmaxf(S.peakNeed, (float)(total + 8) / (float)keep);
                     }
@@ -682,46 +705,30 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     if (lane < keep) { S.wUsed[flip ^ 1][lane] = (unsigned short)wu[0]; S.uPend[flip ^ 1][lane] = (unsigned short)uu[0]; }
                     if (lane + 32 < keep) { S.wUsed[flip ^ 1][lane + 32] = (unsigned short)wu[1]; S.uPend[flip ^ 1][lane + 32] = (unsigned short)uu[1]; }
                 }
-                // list of the generators just appended (cell, row, column in the layout after the next product)
-                int ub0 = lane < keep ? uu[0] : 0, ub1 = lane + 32 < keep ? uu[1] : 0;
-                {
-                    int s0 = ub0, s1 = ub1;
-#pragma unroll
-                    for (int dd = 1; dd < 32; dd <<= 1) {
-                        int t0 = __shfl_up_sync(0xffffffffu, s0, dd);
-                        int t1 = __shfl_up_sync(0xffffffffu, s1, dd);
-                        if (lane >= dd) { s0 += t0; s1 += t1; }
-                    }
-                    const int tot0 = __shfl_sync(0xffffffffu, s0, 31);
-                    const int nIt = tot0 + __shfl_sync(0xffffffffu, s1, 31);
-                    ub0 = s0 - ub0; ub1 = tot0 + s1 - ub1;      // first item of cells lane, lane + 32
-                    if (tid == 0) S.nItems = nIt;
-                    if (nIt <= DZ_ITEMS_MAX) {
-                        for (int ci = warp; ci < keep; ci += nWarps) {
-                            const int nb = ci < 32 ? __shfl_sync(0xffffffffu, off0, ci & 31) : __shfl_sync(0xffffffffu, off1, ci & 31);
-                            const int wuse = ci < 32 ? __shfl_sync(0xffffffffu, wu[0], ci & 31) : __shfl_sync(0xffffffffu, wu[1], ci & 31);
-                            const int base = ci < 32 ? __shfl_sync(0xffffffffu, ub0, ci & 31) : __shfl_sync(0xffffffffu, ub1, ci & 31);
-                            int before = 0;
-                            for (int ww = 0; ww < mw; ww++) {
-                                const unsigned bits = fresh[ci][ww];
-                                if ((bits >> lane) & 1u) {
-                                    const int k = before + __popc(bits & ((1u << lane) - 1u));
-                                    S.itemCol[base + k] = (unsigned short)(nb + wuse + k);
-                                    S.itemCell[base + k] = (unsigned short)ci;
-                                    S.itemRow[base + k] = (unsigned short)(ww * 32 + lane);
-                                }
-                                before += __popc(bits);
-                            }
-                        }
-                    }
-                }
-                // position table: cells dealt to the warps, lanes over a cell's columns
+                // per cell (dealt to the warps, lanes over columns / rows): the position table and the list of the
+                // generators just appended (cell, row, column in the layout after the next product)
+                const bool listItems = nIt <= DZ_ITEMS_MAX;
                 for (int ci = warp; ci < keep; ci += nWarps) {
-                    const int nb = ci < 32 ? __shfl_sync(0xffffffffu, off0, ci & 31) : __shfl_sync(0xffffffffu, off1, ci & 31);
-                    const int wuse = ci < 32 ? __shfl_sync(0xffffffffu, wu[0], ci & 31) : __shfl_sync(0xffffffffu, wu[1], ci & 31);
+                    const int src = ci & 31;
+                    const int nb = ci < 32 ? __shfl_sync(0xffffffffu, off0, src) : __shfl_sync(0xffffffffu, off1, src);
+                    const int wuse = ci < 32 ? __shfl_sync(0xffffffffu, wu[0], src) : __shfl_sync(0xffffffffu, wu[1], src);
+                    const int base = ci < 32 ? __shfl_sync(0xffffffffu, ub0, src) : __shfl_sync(0xffffffffu, ub1, src);
                     const int cb = colOff[ci], wa = colOff[ci + 1] - cb;
                     for (int j = lane; j < wa; j += 32)
                         S.colPos[cb + j] = j < wuse ? (unsigned short)((nb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
+                    if (listItems) {
+                        int before = 0;
+                        for (int ww = 0; ww < mw; ww++) {
+                            const unsigned bits = fresh[ci][ww];
+                            if ((bits >> lane) & 1u) {
+                                const int k = before + __popc(bits & ((1u << lane) - 1u));
+                                S.itemCol[base + k] = (unsigned short)(nb + wuse + k);
+                                S.itemCell[base + k] = (unsigned short)ci;
+                                S.itemRow[base + k] = (unsigned short)(ww * 32 + lane);
+                            }
+                            before += __popc(bits);
+                        }
+                    }
                 }
                 nCells = keep;
             }
