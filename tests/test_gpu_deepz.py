@@ -377,3 +377,53 @@ def test_device_resident_io_and_two_contexts(ctx):
         assert ctx2.launch_count > 0 and ctx2.stream != ctx.stream
     finally:
         ctx2.close()
+
+
+def test_random_networks_fuzz(ctx):
+    """Differential fuzz (random_control_problems recipe, src/utils.jl:34-90, widened): random depths, widths,
+    activations, pre- and post-processing, box and zonotope cells -- every combination against the oracle."""
+    import clr_b200
+    from clr_b200 import workloads
+    rng = np.random.default_rng(2024)
+    acts = ["Id", "ReLU", "Sigmoid", "Tanh"]
+    for trial in range(36):
+        depth = int(rng.integers(1, 6))
+        n_in = int(rng.integers(1, 9))
+        dims = [n_in] + [int(rng.choice([1, 2, 3, 7, 8, 9, 16, 20, 33, 64, 100, 130])) for _ in range(depth)]
+        layers = []
+        for l in range(depth):
+            W = rng.uniform(-1, 1, (dims[l + 1], dims[l])) * np.sqrt(3.0 / dims[l])
+            b = rng.uniform(-0.3, 0.3, dims[l + 1])
+            layers.append((W, b, str(rng.choice(acts))))
+        net = clr_b200.FeedforwardNetwork.from_tuples(layers)
+        pre = None
+        n0 = n_in
+        if trial % 3 == 1:
+            n0 = int(rng.integers(1, 7))
+            pre = (rng.uniform(-1, 1, (n_in, n0)), rng.uniform(-1, 1, n_in))
+        m = dims[-1]
+        post = [None, ("shift", 0.75), ("scale", -1.5), ("matrix", rng.uniform(-1, 1, (int(rng.integers(1, 4)), m))),
+                ("project", sorted(rng.choice(m, size=min(m, 2), replace=False).tolist()))][trial % 5]
+        dn = ctx.upload(net)
+        on = _oracle().Net(net.as_tuples())
+        if trial % 2 == 0:
+            lo = rng.uniform(-1, 0, n0)
+            hi = lo + rng.uniform(0.0, 0.3, n0) * (rng.random(n0) > 0.2)        # some flat dimensions
+            part = [int(rng.integers(1, 4)) for _ in range(n0)]
+            g = clr_b200.split_box(lo, hi, part)
+            got = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, pre=pre, post=post, keep_cap=1200, hull=True)
+            ref = _oracle().deepz_boxgrid(on, g.partition, g.centers, g.radii, pre=pre, post=post, keep_cap=1200)
+        else:
+            C, off, G = workloads.random_zonotopes(rng, 40, n0, 0, 9, -0.8, 0.8, 0.05)
+            got = ctx.deepz_zonotopes(dn, C, off, G, pre=pre, post=post, keep_cap=1200, hull=True)
+            ref = _oracle().deepz_zonotopes(on, C, off, G, pre=pre, post=post, keep_cap=1200)
+        scale = max(1.0, np.abs(ref["hi"]).max(), np.abs(ref["lo"]).max())
+        info = (trial, dims, [a for (_, _, a) in layers], pre is not None, post and post[0])
+        np.testing.assert_allclose(got["lo"], ref["lo"], rtol=0, atol=BOX_ATOL * scale, err_msg=str(info))
+        np.testing.assert_allclose(got["hi"], ref["hi"], rtol=0, atol=BOX_ATOL * scale, err_msg=str(info))
+        assert np.array_equal(got["ncols"], ref["ncols"]), info
+        assert got["stats"]["sum_unstable"] == ref["stats"]["sum_unstable"], info
+        assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"], info
+        gs = max(np.abs(ref["G"]).max(), np.abs(ref["c"]).max(), 1e-300)
+        np.testing.assert_allclose(np.abs(got["G"]), np.abs(ref["G"]), rtol=0, atol=1e-12 * gs, err_msg=str(info))
+        np.testing.assert_allclose(got["c"], ref["c"], rtol=0, atol=1e-12 * gs, err_msg=str(info))
