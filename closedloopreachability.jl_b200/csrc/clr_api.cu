@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <dlfcn.h>
 #include <limits>
@@ -16,6 +17,9 @@
 
 #include "deepz_launch.h"
 #include "rollout.cuh"
+
+#define CLR_PILOT_CELLS 2048        // cells of the pilot run that orders the neurons
+#define CLR_REORDER_MIN_CELLS 16384 // calls with fewer cells keep the network's own neuron order
 
 namespace {
 
@@ -49,6 +53,8 @@ struct clr_net {
     std::vector<int> dims, act;
     std::vector<std::vector<double>> W, b;
     Compiled* compiled = nullptr;
+    Compiled* compiled_perm = nullptr;        // the same network with reordered neurons (see compile_net_reordered)
+    std::vector<HostLayer> layers_folded;    // layer list of `compiled`
 };
 
 // a run-time compiled plant right-hand side (NVRTC -> cubin -> cudaLibrary), one module per evaluator code, built on demand
@@ -88,6 +94,12 @@ struct clr_ctx {
     int64_t keep_cells = 0;
     int keep_cap = 0, keep_m = 0;
     int* d_err = nullptr;
+    // pilot run of the neuron reordering (see reorder_for_grid)
+    DevCallState* d_state2 = nullptr;
+    int* d_live = nullptr;
+    int* h_live = nullptr;               // pinned
+    long long* d_pilot = nullptr;
+    int reorder = 1;                     // clr_set_reorder
     // optional per-pass timing of the last DeepZ call (clr_set_profiling)
     int profiling = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -234,12 +246,10 @@ int upload(clr_ctx* ctx, Compiled* c, const std::vector<T>& v, const T** out) {
     return 0;
 }
 
-int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Compiled** outc) {
-    std::vector<unsigned char> key = prepost_key(net, pp, n_in);
-    if (net->compiled && net->compiled->key == key) { *outc = net->compiled; return 0; }
-    std::vector<HostLayer> layers;
-    int rc = fold_layers(ctx, net, pp, n_in, layers);
-    if (rc) return rc;
+// Device images of a folded layer list: DMMA fragments, biases, pointwise images.
+int compile_layers(clr_ctx* ctx, const std::vector<HostLayer>& layers, int n_in, const std::vector<unsigned char>& key,
+                   Compiled** outc) {
+    int rc;
     if ((int)layers.size() > CLR_DEV_MAX_LAYERS) return fail(ctx, CLR_ERR_ARG, "too many layers");
     Compiled* c = new Compiled();
     c->key = key;
@@ -355,8 +365,55 @@ int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Com
         e = cudaMemcpy(p, &D, sizeof(DevNet), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { free_compiled(c); return fail(ctx, CLR_ERR_CUDA, "cudaMemcpy(DevNet): %s", cudaGetErrorString(e)); }
     }
+    *outc = c;
+    return 0;
+}
+
+int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Compiled** outc) {
+    std::vector<unsigned char> key = prepost_key(net, pp, n_in);
+    if (net->compiled && net->compiled->key == key) { *outc = net->compiled; return 0; }
+    std::vector<HostLayer> layers;
+    int rc = fold_layers(ctx, net, pp, n_in, layers);
+    if (rc) return rc;
+    Compiled* c = nullptr;
+    if ((rc = compile_layers(ctx, layers, n_in, key, &c))) return rc;
     free_compiled(net->compiled);
+    free_compiled(net->compiled_perm);
     net->compiled = c;
+    net->compiled_perm = nullptr;
+    net->layers_folded = layers;
+    *outc = c;
+    return 0;
+}
+
+// The same network with the neurons of every interior layer reordered (rows of W_l and b_l, columns of W_{l+1}):
+// an equivalent parametrisation; `order[l][i]` = original index of the neuron placed at position i of layer l.
+int compile_net_reordered(clr_ctx* ctx, clr_net* net, int n_in, const std::vector<std::vector<int>>& order, Compiled** outc) {
+    std::vector<unsigned char> key = net->compiled->key;
+    for (const auto& o : order) {
+        const unsigned char* p = (const unsigned char*)o.data();
+        key.insert(key.end(), p, p + sizeof(int) * o.size());
+        key.push_back(0xFF);
+    }
+    if (net->compiled_perm && net->compiled_perm->key == key) { *outc = net->compiled_perm; return 0; }
+    std::vector<HostLayer> layers = net->layers_folded;
+    for (size_t l = 0; l + 1 < layers.size(); l++) {
+        const std::vector<int>& o = order[l];
+        if (o.empty()) continue;
+        HostLayer& A = layers[l];
+        HostLayer& B = layers[l + 1];
+        const std::vector<double> W = A.W, b = A.b, W2 = B.W;
+        for (int i = 0; i < A.m; i++) {
+            A.b[i] = b[o[i]];
+            for (int k = 0; k < A.n; k++) A.W[(size_t)k * A.m + i] = W[(size_t)k * A.m + o[i]];
+            for (int r = 0; r < B.m; r++) B.W[(size_t)i * B.m + r] = W2[(size_t)o[i] * B.m + r];
+        }
+    }
+    Compiled* c = nullptr;
+    int rc = compile_layers(ctx, layers, n_in, key, &c);
+    if (rc) return rc;
+    free_compiled(net->compiled_perm);
+    net->compiled_perm = c;
     *outc = c;
     return 0;
 }
@@ -389,6 +446,65 @@ int launch_deepz(clr_ctx* ctx, bool global, bool stats, int ksreg, int grid, int
     if (e != cudaSuccess) return fail(ctx, CLR_ERR_CUDA, "DeepZ kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
     return 0;
+}
+
+// Neuron reordering for box-grid calls.  With ReLU layers about half of the neurons are inactive on the small region a
+// split covers, and inactive neurons leave all-zero rows, i.e. k-steps of the next layer product that multiply zeros.
+// A pilot run over CLR_PILOT_CELLS cells spread over the WHOLE split (so that every shard of the split derives the same
+// order) counts in how many cells each neuron stays non-zero; the neurons of every interior layer are then sorted by
+// that count (an equivalent reparametrisation of the network: rows of W_l, b_l and columns of W_{l+1}), which moves
+// the dead rows to the end where deepz_kernel skips their k-steps (S.kAct).  Results change only by the summation
+// order inside the next product (~1e-16 relative).
+int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& in_full, long double total_cells, int n_in,
+                     Compiled** outc) {
+    *outc = c;
+    const DevNet& D = c->host;
+    bool any = false;
+    for (int l = 0; l + 1 < D.L; l++) any = any || (D.layer[l].act == CLR_ACT_RELU && D.layer[l].m >= 16);
+    if (!any) return 0;
+    const long long S = (long long)std::min<long double>((long double)CLR_PILOT_CELLS, total_cells);
+    std::vector<long long> ids((size_t)S);
+    for (long long k = 0; k < S; k++) ids[(size_t)k] = (long long)((total_cells * k) / S);
+    CU(cudaMemcpyAsync(ctx->d_pilot, ids.data(), sizeof(long long) * (size_t)S, cudaMemcpyHostToDevice, ctx->stream));
+    DevCallState hs{};
+    hs.n_retry = (unsigned long long)S;
+    CU(cudaMemcpyAsync(ctx->d_state2, &hs, sizeof(DevCallState), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_live, 0, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS, ctx->stream));
+    DeepzInput in = in_full;
+    in.cell_begin = 0;                    // the list holds ids of the whole split
+    in.N = S;
+    DeepzOutput out{};
+    out.liveCount = ctx->d_live;
+    DeepzSched sp{};
+    const size_t meta = dz_meta_bytes(false);
+    sp.cap = (int)(((size_t)ctx->smem_optin - meta) / 8);
+    sp.tile_cells = 0;
+    sp.inplace = c->inplace;
+    sp.pass = 1;                          // list-driven pass: the sample ids are the "retry list"
+    sp.retry_list = ctx->d_pilot;
+    sp.big_list = ctx->d_big;             // overflowing cells are simply not sampled (the list is reset by the real run)
+    DevCallState* saved = ctx->d_state;
+    ctx->d_state = ctx->d_state2;
+    int rc = launch_deepz(ctx, false, false, c->ksreg, (int)std::min<long long>(ctx->sms, S), DZ_THREADS, meta + (size_t)sp.cap * 8,
+                          c->dev, in, out, sp);
+    ctx->d_state = saved;
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->h_live, ctx->d_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<std::vector<int>> order((size_t)D.L);
+    bool changed = false;
+    for (int l = 0; l + 1 < D.L; l++) {
+        const DevLayer& d = D.layer[l];
+        if (d.act != CLR_ACT_RELU || d.m < 16) continue;
+        const int* cnt = ctx->h_live + (size_t)l * CLR_MAX_ROWS;
+        std::vector<int> o(d.m);
+        for (int i = 0; i < d.m; i++) o[i] = i;
+        std::stable_sort(o.begin(), o.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+        for (int i = 0; i < d.m; i++) changed = changed || o[i] != i;
+        order[(size_t)l] = std::move(o);
+    }
+    if (!changed) return 0;
+    return compile_net_reordered(ctx, net, n_in, order, outc);
 }
 
 // Shared driver of clr_deepz_boxgrid / clr_deepz_zonotopes once `in` points at device inputs.
@@ -579,6 +695,10 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state2, sizeof(DevCallState));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_pilot, sizeof(long long) * CLR_PILOT_CELLS);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e != cudaSuccess) {
         int rc = fail(nullptr, CLR_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
@@ -604,6 +724,10 @@ void clr_destroy(clr_ctx* ctx) {
     cudaFree(ctx->d_keepC);
     cudaFree(ctx->d_keepG);
     cudaFree(ctx->d_err);
+    cudaFree(ctx->d_state2);
+    cudaFree(ctx->d_live);
+    cudaFreeHost(ctx->h_live);
+    cudaFree(ctx->d_pilot);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -653,6 +777,11 @@ int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells) {
     return 0;
 }
 
+int32_t clr_set_reorder(clr_ctx* ctx, int32_t on) {
+    if (!ctx) return CLR_ERR_ARG;
+    ctx->reorder = on != 0;
+    return 0;
+}
 int32_t clr_set_profiling(clr_ctx* ctx, int32_t on) {
     if (!ctx) return CLR_ERR_ARG;
     ctx->profiling = on != 0;
@@ -702,6 +831,7 @@ void clr_net_free(clr_net* net) {
     if (!net) return;
     if (net->ctx) cudaSetDevice(net->ctx->device);
     free_compiled(net->compiled);
+    free_compiled(net->compiled_perm);
     delete net;
 }
 
@@ -736,6 +866,17 @@ int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net_c, int32_t n, const i
     if ((rc = stage_in(ctx, 1, radii, sizeof(double) * tab, dev_io, &dr))) return rc;
     in.kind = 0; in.n = n; in.N = cell_count; in.cell_begin = cell_begin;
     in.centers = (const double*)dc; in.radii = (const double*)dr;
+    if (ctx->reorder && keep_cap == 0 && cell_count >= CLR_REORDER_MIN_CELLS) {
+        if (cell_count > ctx->list_cap) {       // the pilot borrows the large-cell list of the real run
+            if (ctx->d_retry) CU(cudaFree(ctx->d_retry));
+            if (ctx->d_big) CU(cudaFree(ctx->d_big));
+            ctx->d_retry = ctx->d_big = nullptr; ctx->list_cap = 0;
+            CU(cudaMalloc((void**)&ctx->d_retry, sizeof(long long) * (size_t)cell_count));
+            CU(cudaMalloc((void**)&ctx->d_big, sizeof(long long) * (size_t)cell_count));
+            ctx->list_cap = cell_count;
+        }
+        if ((rc = reorder_for_grid(ctx, net, c, in, total, n, &c))) return rc;
+    }
     return run_deepz(ctx, net, c, in, n, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags);
 }
 

@@ -100,12 +100,13 @@ __device__ __forceinline__ void dz_load_a(const DevLayer& L, int warp, int lane,
 // Bias is added by the relaxation, or here on the centre columns for layers without one.
 // ---------------------------------------------------------------------------------------------
 template <int KSREG>
-__device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, double* Y, int P, int nCols,
+__device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, double* Y, int P, int nCols, int kAct,
                                         const unsigned short* colPos, bool addBias, bool inplace,
                                         int warp, int lane, int nWarps,
                                         double (&a)[KSREG]) {
     constexpr int NB = DZ_NB;                   // column blocks (8 columns each) per group
     const int RB = L.rblocks, KS = L.ksteps;
+    const int ksEff = min(KS, (kAct + 3) >> 2);    // rows >= kAct of every column are zero: their k-steps are skipped
     const int CG = (nCols + 8 * NB - 1) / (8 * NB);
     const int rowsW = clr_pad4(L.m);            // rows written (pad rows of W are zero)
     const int qr = lane >> 2, qc = lane & 3;
@@ -140,6 +141,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                     // full group, whole row block: no predicates, so the loads run ahead of the tensor pipe
 #pragma unroll
                     for (int k = 0; k < KSREG; k++) {
+                        if (k >= ksEff) break;
 #pragma unroll
                         for (int j = 0; j < NB; j++) {
                             const double b = xb[j * 8 * P + k * 4];
@@ -152,14 +154,17 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                         double e0 = 0.0, e1 = 0.0;     // k ascending: the same sums as every other path
                         const double* xs = xb + jj * 8 * P;
 #pragma unroll
-                        for (int k = 0; k < KSREG; k++) dmma884(e0, e1, a[k], xs[k * 4]);
+                        for (int k = 0; k < KSREG; k++) {
+                            if (k >= ksEff) break;
+                            dmma884(e0, e1, a[k], xs[k * 4]);
+                        }
 #pragma unroll
                         for (int j = 0; j < NB; j++) if (j == jj) { d[j][0] = e0; d[j][1] = e1; }
                     }
                 } else if (resident) {
 #pragma unroll
                     for (int k = 0; k < KSREG; k++) {
-                        if (k < KS) {
+                        if (k < ksEff) {
 #pragma unroll
                             for (int j = 0; j < NB; j++) {
                                 if (j < nbAct && ((blkMask >> j) & 1u)) {
@@ -170,7 +175,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                         }
                     }
                 } else {
-                    for (int k = 0; k < KS; k++) {      // wide-K layers: stream the A fragments
+                    for (int k = 0; k < ksEff; k++) {   // wide-K layers: stream the A fragments
                         double av = __ldg(Af + k * 32);
 #pragma unroll
                         for (int j = 0; j < NB; j++) {
@@ -425,6 +430,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 if (lane + 32 < keep) { S.colOff[0][lane + 32] = off1; S.colOff[1][lane + 32] = off1; S.wUsed[0][lane + 32] = (unsigned short)wu1; S.uPend[0][lane + 32] = 0; }
                 if (lane == 0) {
                     S.colOff[0][keep] = total; S.colOff[1][keep] = total; S.nItems = 0;
+                    S.kAct = in.kind == 0 ? S.layers[0].m : n;
                     if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
                     if (keep > 0) S.peakNeed = (float)(total + 8) / (float)keep;
                 }
@@ -510,7 +516,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             const bool relax = !(act == CLR_ACT_ID && !collapse);
             const int m = Ly.m, rowsP = clr_pad4(m), mw = (m + 31) >> 5;
             if (!(l == 0 && in.kind == 0))   // box cells enter with the first layer's product already applied
-                dz_gemm<KSREG>(Ly, cur, oth, P, nCols, S.colPos, !relax, inplace, warp, lane, nWarps, a);
+                dz_gemm<KSREG>(Ly, cur, oth, P, nCols, S.kAct, S.colPos, !relax, inplace, warp, lane, nWarps, a);
             DZ_T(1);
             // Pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i].  In place this is safe
             // without another barrier: after the last group's barrier of the sweep every warp has read every column.
@@ -574,6 +580,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 }
             }
             for (int i = tid; i < nCells * CLR_MASK_WORDS; i += NT) (&fresh[0][0])[i] = 0;
+            if (tid == 0) S.kActNew = 0;
             // weights of the next layer (or of the first layer for the next tile) while the relaxation runs
             dz_load_a<KSREG>(S.layers[l + 1 < L ? l + 1 : 0], warp, lane, nWarps, a);
             if (needDead) {
@@ -597,6 +604,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             if (relax) {
                 const int G = NT / rowsP;                 // cell slots processed side by side
                 const int slot = tid / rowsP, r = tid - slot * rowsP;
+                unsigned rowLive = 0;                     // 1 + the highest row this thread left non-zero
                 if (slot < G && r < m) {
                     const double bias = __ldg(Ly.bias + r);
                     for (int ci = slot; ci < nCells; ci += G) {
@@ -638,6 +646,10 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                                 unst = true;
                             }
                         }
+                        if (cn != 0.0 || la != 0.0) {
+                            rowLive = r + 1;
+                            if (out.liveCount) atomicAdd(&out.liveCount[l * CLR_MAX_ROWS + r], 1);
+                        }
                         y[0] = cn;
                         if (collapse) y[P] = la * rad;       // LazySets' one-row linear_map: a single generator
                         else if (la == 0.0) { for (int j = 1; j < w; j++) y[j * P] = 0.0; }     // inactive row: exactly zero, no reads
@@ -648,7 +660,11 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         }
                     }
                 }
+                rowLive = __reduce_max_sync(0xffffffffu, rowLive);
+                if (lane == 0 && rowLive) atomicMax(&S.kActNew, (int)rowLive);
                 __syncthreads();   // [2]
+            } else if (tid == 0) {
+                S.kActNew = m;                            // no relaxation: every row may be non-zero
             }
             DZ_T(3);
             // ---- next layout (every warp computes it; warp 0 publishes it) and the position table -----------------------
@@ -698,6 +714,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     if (lane == 0) {
                         cn[keep] = total;
                         S.nItems = nIt;
+                        S.kAct = S.kActNew;
                         if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
                         if (keep > 0) S.peakNeed = fmaxf(S.peakNeed, (float)(total + 8) / (float)keep);
                     }

@@ -27,6 +27,7 @@ struct DeepzOutput {
     int* keepN;               // N
     double* keepC;            // m_out x N
     double* keepG;            // m_out x keep_cap x N
+    int* liveCount;           // pilot runs: [layer][CLR_MAX_ROWS] cells in which the neuron was left non-zero, or nullptr
 };
 
 struct DeepzSched {
@@ -43,6 +44,9 @@ struct DeepzSched {
 
 struct DeepzSmem {
     int nCells, tileT, more;
+    int kActNew;                              // being collected by the current relaxation
+    int kAct;                                 // rows of the store that can be non-zero: the next product's K (inactive
+                                              // neurons at the end of a layer are skipped, see dz_gemm)
     int sMaxP;
     long long firstIdx;
     float peakNeed;

@@ -111,6 +111,11 @@ int32_t clr_memcpy_h2d(clr_ctx* ctx, void* dst, const void* src, int64_t bytes);
 int32_t clr_memcpy_d2h(clr_ctx* ctx, void* dst, const void* src, int64_t bytes);
 /* tuning knob of the DeepZ tile scheduler: cells per tile (0 = automatic) */
 int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells);
+/* Neuron reordering of large box-grid calls (default on): a pilot run over 2048 cells of the WHOLE split counts how often
+   each hidden neuron stays non-zero; calls with >= 16384 cells and keep_cap == 0 then run an equivalent network whose
+   inactive neurons come last, so that the layer products skip their all-zero rows.  Results agree with the unordered
+   network to ~1e-16 relative (summation order); every shard of one split uses the same order. */
+int32_t clr_set_reorder(clr_ctx* ctx, int32_t on);
 /* on: CUDA events bracket each pass of the following DeepZ calls (main, retry, big-cell) */
 int32_t clr_set_profiling(clr_ctx* ctx, int32_t on);
 /* device time (ms) of the three passes of the last DeepZ call (needs profiling on), the number of
