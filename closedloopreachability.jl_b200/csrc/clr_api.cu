@@ -478,7 +478,8 @@ int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& 
     DeepzSched sp{};
     const size_t meta = dz_meta_bytes(false);
     sp.cap = (int)(((size_t)ctx->smem_optin - meta) / 8);
-    sp.tile_cells = 0;
+    sp.tile_cells = 4;                    // fixed tiles: which cells a tile drops must not depend on the scheduling,
+                                          // or the order (and the last bits of the results) would vary from call to call
     sp.inplace = c->inplace;
     sp.pass = 1;                          // list-driven pass: the sample ids are the "retry list"
     sp.retry_list = ctx->d_pilot;
