@@ -17,6 +17,7 @@
 
 #include "deepz_launch.h"
 #include "rollout.cuh"
+#include "reduce.cuh"
 
 #define CLR_PILOT_CELLS 2048        // cells of the pilot run that orders the neurons
 #define CLR_REORDER_MIN_CELLS 16384 // calls with fewer cells keep the network's own neuron order
@@ -940,6 +941,48 @@ int32_t clr_deepz_fetch_zonotopes(clr_ctx* ctx, int32_t* out_ncols, double* out_
         size_t k = (size_t)out_ncols[i];
         if (k < cap) memset(out_G + (i * cap + k) * m, 0, sizeof(double) * (cap - k) * m);
     }
+    return 0;
+}
+
+int32_t clr_deepz_fetch_reduced(clr_ctx* ctx, int32_t order, double* out_c, double* out_G, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (ctx->keep_cells <= 0) return fail(ctx, CLR_ERR_STATE, "no kept zonotopes: run a DeepZ call with keep_cap > 0 first");
+    if (!out_c || !out_G) return fail(ctx, CLR_ERR_ARG, "clr_deepz_fetch_reduced: NULL argument");
+    if (order < 1) return fail(ctx, CLR_ERR_ARG, "the target order should be at least 1, but it is %d", order);
+    CU(cudaSetDevice(ctx->device));
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    const size_t N = (size_t)ctx->keep_cells, m = (size_t)ctx->keep_m;
+    const size_t bc = sizeof(double) * m * N, bg = sizeof(double) * m * m * (size_t)order * N;
+    ReduceArgs A;
+    A.N = (long long)N; A.m = (int)m; A.cap = ctx->keep_cap; A.order = order;
+    A.keepN = ctx->d_keepN; A.keepC = ctx->d_keepC; A.keepG = ctx->d_keepG; A.error = ctx->d_err;
+    if (dev_io) { A.outC = out_c; A.outG = out_G; }
+    else {
+        int rc;
+        if ((rc = ensure(ctx, &ctx->d_io[6], &ctx->io_bytes[6], bc))) return rc;
+        if ((rc = ensure(ctx, &ctx->d_io[7], &ctx->io_bytes[7], bg))) return rc;
+        A.outC = (double*)ctx->d_io[6]; A.outG = (double*)ctx->d_io[7];
+    }
+    const size_t smem = (size_t)RD_WARPS * A.cap * (sizeof(double) + sizeof(int));
+    if (smem > (size_t)ctx->smem_optin) return fail(ctx, CLR_ERR_CAPACITY, "keep_cap = %d is too large for the order reduction", A.cap);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(reduce_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    const long long want = ((long long)N + RD_WARPS - 1) / RD_WARPS;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)ctx->smem_optin / (smem + 1024)));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sms * per_sm));
+    reduce_order_kernel<<<grid, RD_WARPS * 32, smem, ctx->stream>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dev_io) {
+        CU(cudaMemcpyAsync(out_c, A.outC, bc, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_G, A.outG, bg, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (err)
+        return fail(ctx, CLR_ERR_DIM, "order-%d reduction needs at least %d generators per zonotope (the reference's reduce_order "
+                    "indexes past the end there)", order, (int)m * (order - 1));
     return 0;
 }
 

@@ -452,10 +452,31 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 double* dst = inplace ? cur : oth;
                 const int G0 = NT / rowsP0, slot = tid / rowsP0, r = tid - slot * rowsP0;
                 if (slot < G0) {
+                    // this thread's row of W (the same for every cell): fetched once, ahead of the cell loop
+                    double wr[8];
+#pragma unroll
+                    for (int d = 0; d < 8; d++) wr[d] = (d < n && r < m0) ? __ldg(L0.Wcm + (size_t)d * m0 + r) : 0.0;
+                    const double b0 = (bias0 && r < m0) ? __ldg(L0.bias + r) : 0.0;
                     for (int ci = slot; ci < nCells; ci += G0) {
                         const int cb = colOff[ci];
                         double* y = dst + cb * P + r;
-                        if (r < m0) {
+                        if (r < m0 && n <= 8) {
+                            const double* cc = tmpC + ci * n;
+                            const double* rr = tmpR + ci * n;
+                            double cv[8], rv[8];
+#pragma unroll
+                            for (int d = 0; d < 8; d++) { cv[d] = d < n ? cc[d] : 0.0; rv[d] = d < n ? rr[d] : 0.0; }
+                            double sacc = 0.0;
+                            int j = 1;
+#pragma unroll
+                            for (int d = 0; d < 8; d++) {
+                                if (d < n) {
+                                    sacc += wr[d] * cv[d];
+                                    if (rv[d] != 0.0) { y[j * P] = wr[d] * rv[d]; j++; }
+                                }
+                            }
+                            y[0] = bias0 ? sacc + b0 : sacc;
+                        } else if (r < m0) {
                             const double* cc = tmpC + ci * n;
                             const double* rr = tmpR + ci * n;
                             double sacc = 0.0;
@@ -602,61 +623,99 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
 
             // ---- relaxation: bounds, lambda, mu, rows scaled in place; thread = (cell slot, row) ------------------------
             if (relax) {
-                const int G = NT / rowsP;                 // cell slots processed side by side
-                const int slot = tid / rowsP, r = tid - slot * rowsP;
                 unsigned rowLive = 0;                     // 1 + the highest row this thread left non-zero
-                if (slot < G && r < m) {
-                    const double bias = __ldg(Ly.bias + r);
-                    for (int ci = slot; ci < nCells; ci += G) {
-                        const int w = wCur[ci] + S.uPend[flip][ci];
-                        const int cb = colOff[ci];
-                        double* y = cur + cb * P + r;
-                        double c = y[0] + bias, lo, hi, rad = 0.0;
-                        if (collapse) {
-                            for (int j = 1; j < w; j++) rad += fabs(y[j * P]);
-                            lo = c - rad; hi = c + rad;
-                        } else {
-                            lo = c; hi = c;
-                            for (int j = 1; j < w; j++) { double av = fabs(y[j * P]); lo -= av; hi += av; }
+                // the activation rule of one neuron: bounds -> (new centre, slope, new generator)
+                auto rule = [&](double c, double lo, double hi, double& cn, double& la, double& mm) -> bool {
+                    cn = c; la = 1.0; mm = 0.0;
+                    if (act == CLR_ACT_RELU) {
+                        if (dz_leq(lo, 0.0)) {
+                            if (dz_leq(hi, 0.0)) { cn = 0.0; la = 0.0; }
+                            else {
+                                la = hi / (hi - lo);
+                                mm = -la * lo / 2;
+                                cn = c * la + mm;
+                                return true;
+                            }
                         }
-                        bool unst = false;
-                        double cn = c, la = 1.0, mm = 0.0;
-                        if (act == CLR_ACT_RELU) {
-                            if (STATS && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
-                            if (dz_leq(lo, 0.0)) {
-                                if (dz_leq(hi, 0.0)) { cn = 0.0; la = 0.0; }
-                                else {
-                                    la = hi / (hi - lo);
-                                    mm = -la * lo / 2;
-                                    cn = c * la + mm;
-                                    unst = true;
+                    } else if (act == CLR_ACT_SIGMOID || act == CLR_ACT_TANH) {
+                        double ly = act == CLR_ACT_SIGMOID ? dz_sigm(lo) : tanh(lo);
+                        double uy = act == CLR_ACT_SIGMOID ? dz_sigm(hi) : tanh(hi);
+                        if (dz_approx(lo, hi)) { cn = uy; la = 0.0; }
+                        else {
+                            double dl = act == CLR_ACT_SIGMOID ? dz_sigm_p(lo) : dz_tanh_p(lo);
+                            double du = act == CLR_ACT_SIGMOID ? dz_sigm_p(hi) : dz_tanh_p(hi);
+                            la = dl < du ? dl : du;
+                            double mu1 = (uy + ly - la * (hi + lo)) / 2;
+                            mm = (uy - ly - la * (hi - lo)) / 2;
+                            cn = c * la + mu1;
+                            return true;
+                        }
+                    }
+                    return false;
+                };
+                {
+                    const int G = NT / rowsP;                 // cell slots processed side by side
+                    const int slot = tid / rowsP, r = tid - slot * rowsP;
+                    if (slot < G && r < m) {
+                        const double bias = __ldg(Ly.bias + r);
+                        for (int ci = slot; ci < nCells; ci += G) {
+                            const int w = wCur[ci] + S.uPend[flip][ci];
+                            const int cb = colOff[ci];
+                            double* y = cur + cb * P + r;
+                            // the row is read in chunks of 8 generators, all loads of a chunk in flight before the (sequential,
+                            // reference-ordered) sums; the first chunk stays in registers for the scaling below
+                            double v[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q++) v[q] = q + 1 < w ? y[(q + 1) * P] : 0.0;
+                            double c = y[0] + bias, lo, hi, rad = 0.0;
+                            if (collapse) {
+#pragma unroll
+                                for (int q = 0; q < 8; q++) rad += fabs(v[q]);       // + 0.0 beyond w: exact
+                                for (int j0 = 9; j0 < w; j0 += 8) {
+                                    double t[8];
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) rad += fabs(t[q]);
+                                }
+                                lo = c - rad; hi = c + rad;
+                            } else {
+                                lo = c; hi = c;
+#pragma unroll
+                                for (int q = 0; q < 8; q++) { const double av = fabs(v[q]); lo -= av; hi += av; }
+                                for (int j0 = 9; j0 < w; j0 += 8) {
+                                    double t[8];
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) { const double av = fabs(t[q]); lo -= av; hi += av; }
                                 }
                             }
-                        } else if (act == CLR_ACT_SIGMOID || act == CLR_ACT_TANH) {
-                            double ly = act == CLR_ACT_SIGMOID ? dz_sigm(lo) : tanh(lo);
-                            double uy = act == CLR_ACT_SIGMOID ? dz_sigm(hi) : tanh(hi);
-                            if (dz_approx(lo, hi)) { cn = uy; la = 0.0; }
-                            else {
-                                double dl = act == CLR_ACT_SIGMOID ? dz_sigm_p(lo) : dz_tanh_p(lo);
-                                double du = act == CLR_ACT_SIGMOID ? dz_sigm_p(hi) : dz_tanh_p(hi);
-                                la = dl < du ? dl : du;
-                                double mu1 = (uy + ly - la * (hi + lo)) / 2;
-                                mm = (uy - ly - la * (hi - lo)) / 2;
-                                cn = c * la + mu1;
-                                unst = true;
+                            if (STATS && act == CLR_ACT_RELU && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
+                            double cn, la, mm;
+                            const bool unst = rule(c, lo, hi, cn, la, mm);
+                            if (cn != 0.0 || la != 0.0) {
+                                rowLive = r + 1;
+                                if (out.liveCount) atomicAdd(&out.liveCount[l * CLR_MAX_ROWS + r], 1);
                             }
-                        }
-                        if (cn != 0.0 || la != 0.0) {
-                            rowLive = r + 1;
-                            if (out.liveCount) atomicAdd(&out.liveCount[l * CLR_MAX_ROWS + r], 1);
-                        }
-                        y[0] = cn;
-                        if (collapse) y[P] = la * rad;       // LazySets' one-row linear_map: a single generator
-                        else if (la == 0.0) { for (int j = 1; j < w; j++) y[j * P] = 0.0; }     // inactive row: exactly zero, no reads
-                        else if (la != 1.0) { for (int j = 1; j < w; j++) y[j * P] = y[j * P] * la; }
-                        if (unst) {
-                            stage[ci * stageW + r] = mm;
-                            atomicOr(&fresh[ci][r >> 5], 1u << (r & 31));
+                            y[0] = cn;
+                            if (collapse) y[P] = la * rad;       // LazySets' one-row linear_map: a single generator
+                            else if (la == 0.0) { for (int j = 1; j < w; j++) y[j * P] = 0.0; }     // inactive row: exactly zero, no reads
+                            else if (la != 1.0) {
+#pragma unroll
+                                for (int q = 0; q < 8; q++) if (q + 1 < w) y[(q + 1) * P] = v[q] * la;
+                                for (int j0 = 9; j0 < w; j0 += 8) {
+                                    double t[8];
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) if (j0 + q < w) y[(j0 + q) * P] = t[q] * la;
+                                }
+                            }
+                            if (unst) {
+                                stage[ci * stageW + r] = mm;
+                                atomicOr(&fresh[ci][r >> 5], 1u << (r & 31));
+                            }
                         }
                     }
                 }

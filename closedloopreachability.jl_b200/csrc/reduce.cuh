@@ -1,0 +1,86 @@
+// reduce.cuh -- batched order reduction of the kept output zonotopes (Girard's method, GIR05).
+//
+// Replaces, for all cells of a control step at once, the per-cell
+//     Z0 = _reduce_order(_convert_or_overapproximate(U0, Zonotope), 2; force_reduction=true)
+// of TaylorModelReconstructor(box=false) (reference src/setops.jl:84-86), i.e. LazySets'
+// reduce_order(Z, r, GIR05()): the generators are ordered by decreasing  |g|_1 - |g|_inf  (stable: ties keep
+// their original order), the first  kept = m (r - 1)  are kept as they are and the others are replaced by their
+// interval hull, a diagonal block whose entry i is the sum of |G[i, j]| over the boxed generators IN SORTED ORDER
+// (the loop of _interval_hull).  The result has exactly m r generators: [G[:, kept ones] | diag(d)], the layout
+// src/setops.jl:96-101 asserts (size (m, 2m), diagonal tail).  r = 1 boxes everything without sorting.
+//
+// One warp per cell.  HBM-bound streaming kernel: 8 m (1 + p) bytes read and 8 m (1 + m r) bytes written per cell;
+// the weights and the sorted order live in shared memory, the generators are re-read through L1.
+#pragma once
+#include "common.cuh"
+
+struct ReduceArgs {
+    long long N;
+    int m, cap, order;        // rows, generator capacity of keepG, target order r
+    const int* keepN;         // N generator counts
+    const double* keepC;      // m x N
+    const double* keepG;      // m x cap x N
+    double* outC;             // m x N
+    double* outG;             // m x (m r) x N
+    int* error;               // set to 1 when a cell has fewer than m (r - 1) generators
+};
+
+#define RD_WARPS 4
+
+__global__ void __launch_bounds__(RD_WARPS * 32) reduce_order_kernel(ReduceArgs A) {
+    extern __shared__ __align__(16) unsigned char rd_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* wgt = reinterpret_cast<double*>(rd_smem) + (size_t)warp * A.cap;
+    int* sorted = reinterpret_cast<int*>(rd_smem + sizeof(double) * (size_t)RD_WARPS * A.cap) + (size_t)warp * A.cap;
+    const int m = A.m, kept = m * (A.order - 1), gout = m * A.order;
+    for (long long cell = (long long)blockIdx.x * RD_WARPS + warp; cell < A.N; cell += (long long)gridDim.x * RD_WARPS) {
+        const int p = A.keepN[cell];
+        const double* G = A.keepG + (size_t)cell * A.cap * m;
+        double* oG = A.outG + (size_t)cell * gout * m;
+        for (int i = lane; i < m; i += 32) A.outC[cell * m + i] = A.keepC[cell * m + i];
+        if (p < kept) {                      // the reference indexes past the end here (BoundsError)
+            if (lane == 0) atomicExch(A.error, 1);
+            continue;
+        }
+        if (kept > 0) {
+            // weights: |g|_1 (summed over the rows in ascending order) minus |g|_inf
+            for (int j = lane; j < p; j += 32) {
+                const double* g = G + (size_t)j * m;
+                double s = 0.0, mx = 0.0;
+                for (int i = 0; i < m; i++) { const double a = fabs(g[i]); s += a; mx = fmax(mx, a); }
+                wgt[j] = s - mx;
+            }
+            __syncwarp();
+            // stable descending order by counting: position of j = #{k : w_k > w_j, or w_k == w_j and k < j}
+            for (int j = lane; j < p; j += 32) {
+                const double wj = wgt[j];
+                int pos = 0;
+                for (int k = 0; k < p; k++) { const double wk = wgt[k]; pos += (wk > wj) || (wk == wj && k < j); }
+                sorted[pos] = j;
+            }
+            __syncwarp();
+        }
+        // kept generators, in sorted order
+        for (int t = lane; t < kept * m; t += 32) {
+            const int k = t / m, i = t - k * m;
+            oG[t] = G[(size_t)sorted[k] * m + i];
+        }
+        // interval hull of the others: lane i owns row i; sequential sums in sorted order, 8 loads in flight
+        for (int i = lane; i < m; i += 32) {
+            double d = 0.0;
+            for (int k0 = kept; k0 < p; k0 += 8) {
+                double t[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int k = k0 + q;
+                    t[q] = k < p ? G[(size_t)(kept > 0 ? sorted[k] : k) * m + i] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) d += fabs(t[q]);       // + 0.0 past the end: exact
+            }
+            for (int i2 = 0; i2 < m; i2++) oG[(size_t)(kept + i2) * m + i] = 0.0;
+            oG[(size_t)(kept + i) * m + i] = d;
+        }
+        __syncwarp();
+    }
+}

@@ -284,6 +284,16 @@ class Context:
             self._check(self.L.clr_deepz_fetch_zonotopes(self.h, _ptr(nc), _ptr(c), _ptr(G)))
         return {"ncols": nc, "c": c, "G": G}
 
+    def fetch_reduced(self, N, m, order=2):
+        """Order-`order` Girard reduction of the zonotopes kept by the last keep_cap > 0 run: the
+        Z0 = _reduce_order(U0, 2; force_reduction=true) of TaylorModelReconstructor(box=false)
+        (reference src/setops.jl:84-86) for every cell.  -> c (N, m), G (N, m*order, m): row j = generator j."""
+        c = np.zeros((N, m))
+        G = np.zeros((N, m * order, m))
+        if N > 0:
+            self._check(self.L.clr_deepz_fetch_reduced(self.h, int(order), _ptr(c), _ptr(G), 0))
+        return {"c": c, "G": G}
+
     # device-resident variant: every data pointer is a device pointer / torch CUDA tensor
     def deepz_boxgrid_dev(self, dnet, n, d_partition_host, d_centers, d_radii, cell_begin, cell_count, pp: PrePostArg,
                           d_lo, d_hi, d_hull_lo=None, d_hull_hi=None, stats=None, keep_cap=0):

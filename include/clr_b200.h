@@ -24,6 +24,7 @@
  *                             models/VerticalCAS/VerticalCAS.jl:122 direct forward(Y, net, DeepZ()) calls)
  *   clr_deepz_fetch_zonotopes the output set U of controller_forward (src/solve.jl:213) when the caller
  *                             needs more than its box (TaylorModelReconstructor(box=false), src/setops.jl:84-107)
+ *   clr_deepz_fetch_reduced   _reduce_order(Z0, 2; force_reduction=true) of the same reconstructor, src/setops.jl:84-86
  *   clr_forward_points        forward(x, network) + pre/post-processing, src/simulate.jl:101-106
  *   clr_rollout               the period loop of simulate (src/simulate.jl:98-140) incl. _solve_ensemble
  *                             (ext/ClosedLoopReachabilityOrdinaryDiffEqExt.jl:28-45: Tsit5 ensemble)
@@ -163,6 +164,17 @@ int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net, int32_t n, int64_t
  * ascending neuron order.  HOST pointers.
  */
 int32_t clr_deepz_fetch_zonotopes(clr_ctx* ctx, int32_t* out_ncols, double* out_c, double* out_G);
+
+/*
+ * Order reduction of the kept output zonotopes (Girard's method, LazySets reduce_order(Z, r, GIR05())), for all
+ * cells at once: replaces the per-cell  _reduce_order(Z0, 2; force_reduction=true)  of
+ * TaylorModelReconstructor(box=false) (src/setops.jl:84-86).  The generators are ordered by decreasing
+ * |g|_1 - |g|_inf (stable), the first m (order - 1) are kept, the others are replaced by their interval hull:
+ * out_G (m x (m order) x N) = [kept generators | diag(d)], the layout src/setops.jl:96-101 asserts for order 2;
+ * out_c (m x N).  order = 1 is the box.  A zonotope with fewer than m (order - 1) generators is an error
+ * (CLR_ERR_DIM; the reference throws there).  flags: CLR_FLAG_DEVICE_IO makes out_c / out_G device pointers.
+ */
+int32_t clr_deepz_fetch_reduced(clr_ctx* ctx, int32_t order, double* out_c, double* out_G, int32_t flags);
 
 /* ---- pointwise controller -------------------------------------------------------------------- */
 /* X: nx x N, U: m_out x N */

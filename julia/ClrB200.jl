@@ -111,6 +111,18 @@ function controller_forward_boxes(ctx::Context, dnet::DeviceNetwork, Zs::Abstrac
 end
 
 """
+`TaylorModelReconstructor(box=false)` (src/setops.jl:84-101) for all cells of the last `keep_cap > 0` run at once:
+`Z0 = _reduce_order(U0, 2; force_reduction=true)`.  Returns the centres (m x N) and the generators (m x 2m x N);
+cell i's `M = G[:, 1:m, i]` and diagonal `D = G[:, m+1:2m, i]` are what the loop at src/setops.jl:96-101 reads.
+"""
+function reduced_controls(ctx::Context, m::Integer, N::Integer; order::Integer=2)
+    c = Matrix{Float64}(undef, m, N); G = Array{Float64}(undef, m, m * order, N)
+    check(ctx, ccall((:clr_deepz_fetch_reduced, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int32),
+                     ctx.h, order, c, G, 0))
+    return c, G
+end
+
+"""
 `simulate`'s period loop (src/simulate.jl:98-140) for a built-in plant: x0 is n_state x N, Wd n_dist x N x iters
 (drawn on the Julia side in the reference's RNG order: x0 once, then W0 once per period, src/simulate.jl:89, :111).
 """

@@ -165,6 +165,21 @@ def deepz_zonotopes(net: Net, Cc, col_off, G, pre=None, post=None, keep_cap=0):
     return out
 
 
+def reduce_order(ncols, c, G, order=2):
+    """ncols: (N,), c: (N, m), G: (N, cap, m) as returned with keep_cap; -> (c, G_red (N, m*order, m))."""
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    G = np.ascontiguousarray(G, dtype=np.float64)
+    ncols = np.ascontiguousarray(ncols, dtype=np.int32)
+    N, cap, m = G.shape
+    oc = np.empty((N, m)); oG = np.empty((N, m * order, m))
+    L = lib()
+    L.clro_reduce_order.restype = C.c_int
+    rc = L.clro_reduce_order(m, cap, int(order), C.c_int64(N), _p(ncols), _p(c), _p(G), _p(oc), _p(oG))
+    if rc != 0:
+        raise IndexError(f"clro_reduce_order rc={rc}")
+    return oc, oG
+
+
 def forward_points(net: Net, X, pre=None, post=None):
     X = np.ascontiguousarray(X, dtype=np.float64)
     N, nx = X.shape

@@ -701,3 +701,51 @@ int clro_rollout(const clro_net* net, const clro_prepost* pp, int plant, int n_s
     }
     return 0;
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * TaylorModelReconstructor(box=false): Z0 = _reduce_order(U0, 2; force_reduction=true), reference src/setops.jl:84-86
+ * -> LazySets reduce_order(Z, r, GIR05()) [UPSTREAM-RECALL]: generators ordered by decreasing |g|_1 - |g|_inf (stable),
+ * the first m (r - 1) kept, the others replaced by their interval hull (sums taken in sorted order).
+ * Layouts as clro_deepz_*'s kept zonotopes: ncols (N), G (m x cap x N); outG (m x (m r) x N).
+ * Returns -3 when a zonotope has fewer than m (r - 1) generators (the reference throws).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { double w; int j; } wj_t;
+static int wj_cmp(const void* a, const void* b) {
+    const wj_t* x = (const wj_t*)a; const wj_t* y = (const wj_t*)b;
+    if (x->w > y->w) return -1;
+    if (x->w < y->w) return 1;
+    return x->j - y->j;     /* stable */
+}
+int clro_reduce_order(int m, int cap, int order, int64_t N, const int32_t* ncols, const double* C, const double* G,
+                      double* outC, double* outG) {
+    const int kept = m * (order - 1), gout = m * order;
+    int bad = 0;
+    if (order < 1) return -1;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t cell = 0; cell < N; cell++) {
+        const int p = ncols[cell];
+        const double* g = G + (size_t)cell * cap * m;
+        double* og = outG + (size_t)cell * gout * m;
+        for (int i = 0; i < m; i++) outC[cell * m + i] = C[cell * m + i];
+        if (p < kept) { bad |= 1; continue; }
+        wj_t* ord = (wj_t*)malloc(sizeof(wj_t) * (size_t)(p > 0 ? p : 1));
+        for (int j = 0; j < p; j++) {
+            double s = 0.0, mx = 0.0;
+            for (int i = 0; i < m; i++) { double a = fabs(g[(size_t)j * m + i]); s += a; if (a > mx) mx = a; }
+            ord[j].w = kept > 0 ? s - mx : 0.0;
+            ord[j].j = j;
+        }
+        if (kept > 0) qsort(ord, (size_t)p, sizeof(wj_t), wj_cmp);
+        for (int k = 0; k < kept; k++)
+            for (int i = 0; i < m; i++) og[(size_t)k * m + i] = g[(size_t)ord[k].j * m + i];
+        for (int i = 0; i < m; i++) {
+            double d = 0.0;
+            for (int k = kept; k < p; k++) d += fabs(g[(size_t)ord[k].j * m + i]);
+            for (int i2 = 0; i2 < m; i2++) og[(size_t)(kept + i2) * m + i] = 0.0;
+            og[(size_t)(kept + i) * m + i] = d;
+        }
+        free(ord);
+    }
+    return bad ? -3 : 0;
+}

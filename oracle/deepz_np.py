@@ -9,6 +9,7 @@ Reference call chain restated here
   src/splitters.jl:20-28    BoxSplitter -> LazySets.split(box_approximation(X), partition)
   src/problem.jl:10-58      apply(postprocessing, X::LazySet)
   src/setops.jl:76-83       box_approximation(U0) -- all the default plant step consumes
+  src/setops.jl:84-86       _reduce_order(Z0, 2; force_reduction=true) -- TaylorModelReconstructor(box=false)
 
 Upstream algorithms (recalled; [UPSTREAM-RECALL] in SURVEY.md 8c)
   LazySets  AbstractZonotope: linear_map (incl. _linear_map_zonotope_1D), low/high
@@ -17,6 +18,7 @@ Upstream algorithms (recalled; [UPSTREAM-RECALL] in SURVEY.md 8c)
   ReachabilityBase.Comparison  _leq/_isapprox/isapproxzero (rtol=sqrt(eps), ztol=10eps, atol=0)
   ReachabilityBase.Arrays      remove_zero_columns
   LazySets  AbstractHyperrectangle: split(H, num_blocks), genmat (flat dims dropped)
+  LazySets  reduce_order(Z, r, GIR05()): _weighted_gens!, _interval_hull, _hcat_KLred
 
 A network is a list of layers ``(W, b, act)`` with ``W`` of shape (m, n), ``b`` of
 shape (m,) and ``act`` in {"Id", "ReLU", "Sigmoid", "Tanh"}.
@@ -434,3 +436,43 @@ def split_zonotope(c, G, gens, nparts):
                 nxt += [a, b]
             Zs = nxt
     return Zs
+
+
+# --------------------------------------------------------------------------------------
+# TaylorModelReconstructor(box=false): order reduction of U0      (src/setops.jl:84-101) [UPSTREAM-RECALL]
+# --------------------------------------------------------------------------------------
+def reduce_order_gir05(c, G, r=2):
+    """LazySets reduce_order(Z, r, GIR05()) with ReachabilityAnalysis' force_reduction=true.
+
+    weights_j = norm(g_j, 1) - norm(g_j, Inf); indices = sortperm(weights; rev=true) (stable); the first
+    m*(r-1) generators are kept, the others are replaced by their interval hull, whose diagonal entry i is
+    the sum of |G[i, j]| over the boxed generators in SORTED order (the loop of _interval_hull).
+    Returns (c, [G[:, kept] | diag(d)]) with exactly m*r generators; r == 1 boxes everything unsorted.
+    A zonotope with fewer than m*(r-1) generators raises IndexError (the reference: BoundsError).
+    """
+    c = np.asarray(c, dtype=np.float64)
+    G = np.asarray(G, dtype=np.float64)
+    m, p = G.shape
+    kept = m * (r - 1)
+    if p < kept:
+        raise IndexError(f"order-{r} reduction of a zonotope with {p} < {kept} generators")
+    if kept == 0:
+        order = list(range(p))
+    else:
+        w = []
+        for j in range(p):
+            s1 = 0.0
+            mx = 0.0
+            for i in range(m):
+                a = abs(float(G[i, j]))
+                s1 += a
+                mx = max(mx, a)
+            w.append(s1 - mx)
+        order = sorted(range(p), key=lambda j: -w[j])      # Python's sort is stable, like Julia's sortperm
+    d = np.zeros(m)
+    for i in range(m):
+        acc = 0.0
+        for j in order[kept:]:
+            acc += abs(float(G[i, j]))
+        d[i] = acc
+    return c.copy(), np.hstack([G[:, order[:kept]], np.diag(d)])

@@ -427,3 +427,52 @@ def test_random_networks_fuzz(ctx):
         gs = max(np.abs(ref["G"]).max(), np.abs(ref["c"]).max(), 1e-300)
         np.testing.assert_allclose(np.abs(got["G"]), np.abs(ref["G"]), rtol=0, atol=1e-12 * gs, err_msg=str(info))
         np.testing.assert_allclose(got["c"], ref["c"], rtol=0, atol=1e-12 * gs, err_msg=str(info))
+
+
+def test_order2_reduction_of_kept_zonotopes(ctx):
+    """TaylorModelReconstructor(box=false): Z0 = _reduce_order(U0, 2; force_reduction=true), src/setops.jl:84-86,
+    for every cell of the Quadrotor split (3 outputs, 198 generators each) in one call."""
+    import clr_b200
+    from oracle import deepz_np as dz
+    net = load_net("Quadrotor")
+    dn = ctx.upload(net)
+    r = 0.01 * np.array([0.4] * 6 + [0.0] * 6)
+    g = clr_b200.split_box(-r, r, [2] * 6 + [1] * 6)
+    got = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, keep_cap=256)
+    N, m = got["lo"].shape
+    for order in (2, 1, 3):
+        red = ctx.fetch_reduced(N, m, order)
+        assert red["G"].shape == (N, m * order, m)
+        # (a) against the oracle's reduction of the very same zonotopes: the same sums in the same order -> bit-identical
+        oc, oG = _oracle().reduce_order(got["ncols"], got["c"], got["G"], order)
+        assert np.array_equal(red["c"], oc)
+        assert np.array_equal(red["G"], oG)
+        # (b) against the NumPy restatement on one cell, and the diagonal tail src/setops.jl:96-101 asserts
+        p = got["ncols"][5]
+        _, rG = dz.reduce_order_gir05(got["c"][5], got["G"][5, :p].T, order)
+        assert np.array_equal(red["G"][5].T, rG)
+        D = red["G"][:, m * (order - 1):, :]
+        assert np.count_nonzero(D * (1 - np.eye(m))[None]) == 0
+        # (c) the reduction keeps every cell's box
+        rad = np.abs(red["G"]).sum(axis=1)
+        np.testing.assert_allclose(red["c"] - rad, got["lo"], rtol=0, atol=BOX_ATOL)
+        np.testing.assert_allclose(red["c"] + rad, got["hi"], rtol=0, atol=BOX_ATOL)
+    # (d) end to end against the CPU oracle pipeline (DeepZ + reduction)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii, keep_cap=256)
+    _, refG = _oracle().reduce_order(ref["ncols"], ref["c"], ref["G"], 2)
+    red = ctx.fetch_reduced(N, m, 2)
+    scale = np.abs(refG).max()
+    np.testing.assert_allclose(red["G"], refG, rtol=0, atol=1e-12 * scale)
+
+
+def test_order_reduction_errors(ctx):
+    net = load_net("Quadrotor")
+    dn = ctx.upload(net)
+    c = np.zeros((2, 12)); G = 0.01 * np.eye(12)[:2]          # cells with a single generator
+    r = ctx.deepz_zonotopes(dn, c, [0, 1, 2], G, keep_cap=256)
+    assert r["ncols"].max() >= 3                               # sigmoid layers append generators: order 2 is fine
+    ctx.fetch_reduced(2, 3, 2)
+    with pytest.raises(Exception):
+        ctx.fetch_reduced(2, 3, 200)                           # needs 597 generators: the reference throws here
+    with pytest.raises(Exception):
+        ctx.fetch_reduced(2, 3, 0)

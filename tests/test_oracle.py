@@ -162,3 +162,53 @@ def test_c_oracle_threads_and_flops():
     r = cbind.deepz_boxgrid(cn, [10, 10, 10, 1], cent, radii, post=("shift", -10.0))
     # mean 0.327 MFLOP per cell on this workload
     assert abs(r["stats"]["flops"] / 1000 / 1e6 - 0.327) < 0.002
+
+
+# ---- order reduction of the output zonotope (TaylorModelReconstructor(box=false), src/setops.jl:84-101) ----
+def test_reduce_order_hand_example():
+    # 2-dim zonotope with 5 generators; weights |g|_1 - |g|_inf = [0, 1, 0.5, 0, 0.25]
+    c = np.array([1.0, -1.0])
+    G = np.array([[2.0, 1.0, 0.5, 0.0, -0.25],
+                  [0.0, 3.0, -4.0, 7.0, 1.0]])
+    c2, R = dz.reduce_order_gir05(c, G, 2)
+    assert R.shape == (2, 4) and np.array_equal(c2, c)
+    # kept: generators 2 and 3 (weights 1 and 0.5); boxed in sorted order: 5 (0.25), then 1 and 4 (ties keep their order)
+    assert np.array_equal(R[:, :2], G[:, [1, 2]])
+    assert np.array_equal(R[:, 2:], np.diag([0.25 + 2.0 + 0.0, 1.0 + 0.0 + 7.0]))
+    # the layout src/setops.jl:96-101 asserts: (m, 2m) with a diagonal tail
+    D = R[:, 2:]
+    assert np.count_nonzero(D - np.diag(np.diag(D))) == 0
+    # order 1 = the interval hull, no sorting
+    _, B = dz.reduce_order_gir05(c, G, 1)
+    assert np.array_equal(B, np.diag(np.abs(G).sum(axis=1)))
+    with pytest.raises(IndexError):
+        dz.reduce_order_gir05(c, G[:, :1], 2)
+
+
+@pytest.mark.parametrize("m,order", [(2, 2), (3, 2), (3, 3), (6, 2), (3, 1)])
+def test_reduce_order_numpy_vs_c_and_box_invariance(m, order):
+    rng = np.random.default_rng(100 * m + order)
+    N, cap = 40, 64
+    ncols = rng.integers(m * (order - 1), cap + 1, size=N).astype(np.int32)
+    c = rng.normal(size=(N, m))
+    G = np.zeros((N, cap, m))
+    for i in range(N):
+        G[i, :ncols[i]] = rng.normal(size=(ncols[i], m)) * rng.choice([1.0, 1e-3, 0.0], size=(ncols[i], 1), p=[.7, .2, .1])
+        if ncols[i] > 3:
+            G[i, 2] = G[i, 0]                      # equal weights: the stable order decides
+    oc, oG = cbind.reduce_order(ncols, c, G, order)
+    for i in range(N):
+        p = ncols[i]
+        rc, rG = dz.reduce_order_gir05(c[i], G[i, :p].T, order)
+        assert np.array_equal(oc[i], rc)
+        assert np.array_equal(oG[i].T, rG)          # same sums in the same order: bit-identical
+        # the reduction keeps the box of the zonotope (up to the order of the sums)
+        lo0, hi0 = dz.low_high(c[i], G[i, :p].T)
+        lo1, hi1 = dz.low_high(rc, rG)
+        np.testing.assert_allclose(lo1, lo0, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(hi1, hi0, rtol=0, atol=1e-12)
+    with pytest.raises(IndexError):
+        if order > 1:
+            cbind.reduce_order(np.zeros(1, dtype=np.int32), c[:1], G[:1], order)
+        else:
+            raise IndexError
