@@ -19,6 +19,8 @@
 #include "rollout.cuh"
 #include "reduce.cuh"
 
+#define CLR_BOUNCE_BYTES (1u << 20)  // pinned bounce buffer of the small-call path
+#define CLR_BOUNCE_IN_MAX (256u << 10)
 #define CLR_PILOT_CELLS 2048        // cells of the pilot run that orders the neurons
 #define CLR_REORDER_MIN_CELLS 16384 // calls with fewer cells keep the network's own neuron order
 
@@ -85,6 +87,12 @@ struct clr_ctx {
     // scratch for blocking-mode I/O
     void* d_io[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t io_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // small-call path of the blocking mode: one pinned bounce buffer and its device twin; the inputs of a call (and
+    // the hull seed) go up in ONE copy, the boxes and the hull come back in ONE copy
+    unsigned char* h_bounce = nullptr;   // pinned
+    unsigned char* d_bounce = nullptr;
+    size_t bounce_used = 0, bounce_flushed = 0;
+    bool bounce_open = false;
     double* d_hull = nullptr;            // 2 * m_out
     int hull_cap = 0;
     // kept output zonotopes
@@ -136,6 +144,24 @@ int ensure(clr_ctx* ctx, void** p, size_t* have, size_t need) {
     size_t sz = need + need / 4 + 256;
     CU(cudaMalloc(p, sz));
     *have = sz;
+    return 0;
+}
+
+// reserve `bytes` in the bounce buffer (host pointer returned, device twin at the same offset); nullptr when it does not fit
+void* bounce_take(clr_ctx* ctx, size_t bytes, size_t* off) {
+    const size_t o = (ctx->bounce_used + 255) & ~(size_t)255;
+    if (!ctx->bounce_open || o + bytes > CLR_BOUNCE_BYTES) return nullptr;
+    ctx->bounce_used = o + bytes;
+    *off = o;
+    return ctx->h_bounce + o;
+}
+// everything staged so far goes to the device (one copy for all inputs of a small call)
+int bounce_flush(clr_ctx* ctx) {
+    if (ctx->bounce_used > ctx->bounce_flushed) {
+        const size_t a = ctx->bounce_flushed & ~(size_t)255;
+        CU(cudaMemcpyAsync(ctx->d_bounce + a, ctx->h_bounce + a, ctx->bounce_used - a, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->bounce_flushed = ctx->bounce_used;
+    }
     return 0;
 }
 
@@ -467,6 +493,7 @@ int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& 
     std::vector<long long> ids((size_t)S);
     for (long long k = 0; k < S; k++) ids[(size_t)k] = (long long)((total_cells * k) / S);
     CU(cudaMemcpyAsync(ctx->d_pilot, ids.data(), sizeof(long long) * (size_t)S, cudaMemcpyHostToDevice, ctx->stream));
+    { int rcf = bounce_flush(ctx); if (rcf) return rcf; }     // the split tables of a blocking call
     DevCallState hs{};
     hs.n_retry = (unsigned long long)S;
     CU(cudaMemcpyAsync(ctx->d_state2, &hs, sizeof(DevCallState), cudaMemcpyHostToDevice, ctx->stream));
@@ -523,6 +550,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         if (stats) { memset(stats, 0, sizeof(*stats)); }
         if (!dev_io && hull_lo) for (int i = 0; i < m; i++) { hull_lo[i] = INFINITY; hull_hi[i] = -INFINITY; }
         ctx->keep_cells = 0;
+        ctx->bounce_open = false;
         return 0;
     }
     // device outputs
@@ -538,7 +566,30 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         ctx->hull_cap = m;
     }
     const bool want_hull = hull_lo != nullptr && hull_hi != nullptr;
-    if (want_hull) {
+    // Small blocking calls (the reference's own problem sizes: one to a few thousand cells per control step) are bound by
+    // the number of driver calls, not by the kernel: the hull seed travels with the inputs, and the hull and the boxes
+    // come back in one copy from one contiguous region [hull | lo | hi] of the bounce buffer.
+    size_t fast_off = 0, fast_bytes = 0;
+    bool fast = false;
+    if (!dev_io && ctx->bounce_open && keep_cap == 0) {
+        const size_t hb = want_hull ? sizeof(double) * 2 * (size_t)m : 0;
+        const size_t ob = (out_lo && out_hi) ? sizeof(double) * (size_t)m * (size_t)N : 0;
+        double* hseed = (double*)bounce_take(ctx, hb + 2 * ob + 16, &fast_off);
+        if (hseed) {
+            fast = true;
+            fast_bytes = hb + 2 * ob;
+            for (int i = 0; want_hull && i < m; i++) { hseed[i] = INFINITY; hseed[m + i] = -INFINITY; }
+            ctx->bounce_used = fast_off + hb;          // only the seed has to go up
+            double* dbase = (double*)(ctx->d_bounce + fast_off);
+            if (want_hull) { out.hull_lo = dbase; out.hull_hi = dbase + m; }
+            if (ob) { out.out_lo = dbase + 2 * (want_hull ? m : 0); out.out_hi = out.out_lo + (size_t)m * N; }
+        }
+    }
+    { int rcf = bounce_flush(ctx); if (rcf) return rcf; }
+    ctx->bounce_open = false;
+    if (fast) {
+        // nothing else to set up
+    } else if (want_hull) {
         fill_hull_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_hull, m);
         CU(cudaGetLastError());
         ctx->launches++;
@@ -546,7 +597,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     } else {
         out.hull_lo = nullptr; out.hull_hi = nullptr;
     }
-    if (!dev_io) {
+    if (!dev_io && !fast) {
         if (out_lo && out_hi) {
             int rc;
             if ((rc = ensure(ctx, &ctx->d_io[4], &ctx->io_bytes[4], sizeof(double) * (size_t)m * N))) return rc;
@@ -594,11 +645,23 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 8, c->dev, in, out, sp))) return rc;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
-    if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 8, c->dev, in, out, sp))) return rc;
-    if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    // how many cells did not fit in shared memory at all?
-    CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    bool fast_done = false;
+    if (fast) {
+        // one round trip: scheduler state and results together; the retry pass only runs when a tile overflowed
+        CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
+        if (fast_bytes)
+            CU(cudaMemcpyAsync(ctx->h_bounce + fast_off, ctx->d_bounce + fast_off, fast_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        fast_done = ctx->h_state->n_retry == 0 && ctx->h_state->n_big == 0;
+        if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    }
+    if (!fast || ctx->h_state->n_retry > 0) {
+        if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 8, c->dev, in, out, sp))) return rc;
+        if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        // how many cells did not fit in shared memory at all?
+        CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     if (ctx->profiling) {
         CU(cudaEventElapsedTime(&ctx->pass_ms[0], ctx->ev[0], ctx->ev[1]));
         CU(cudaEventElapsedTime(&ctx->pass_ms[1], ctx->ev[1], ctx->ev[2]));
@@ -644,6 +707,17 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
             CU(cudaMemcpyAsync(hull_lo, ctx->d_hull, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
             CU(cudaMemcpyAsync(hull_hi, ctx->d_hull + m, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
         }
+    } else if (fast) {
+        if (!fast_done && fast_bytes) {
+            CU(cudaMemcpyAsync(ctx->h_bounce + fast_off, ctx->d_bounce + fast_off, fast_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        const double* hb = (const double*)(ctx->h_bounce + fast_off);
+        if (want_hull) { memcpy(hull_lo, hb, sizeof(double) * m); memcpy(hull_hi, hb + m, sizeof(double) * m); hb += 2 * m; }
+        if (out_lo && out_hi) {
+            memcpy(out_lo, hb, sizeof(double) * (size_t)m * N);
+            memcpy(out_hi, hb + (size_t)m * N, sizeof(double) * (size_t)m * N);
+        }
     } else {
         if (out_lo && out_hi) {
             CU(cudaMemcpyAsync(out_lo, out.out_lo, sizeof(double) * (size_t)m * N, cudaMemcpyDeviceToHost, ctx->stream));
@@ -660,6 +734,15 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
 
 int stage_in(clr_ctx* ctx, int slot, const void* src, size_t bytes, bool dev_io, const void** out) {
     if (dev_io) { *out = src; return 0; }
+    if (ctx->bounce_open && bytes <= CLR_BOUNCE_IN_MAX && ctx->bounce_used + bytes + 256 <= CLR_BOUNCE_IN_MAX) {
+        size_t off;
+        void* h = bounce_take(ctx, bytes ? bytes : 8, &off);
+        if (h) {
+            if (bytes) memcpy(h, src, bytes);
+            *out = ctx->d_bounce + off;
+            return 0;
+        }
+    }
     int rc = ensure(ctx, &ctx->d_io[slot], &ctx->io_bytes[slot], bytes ? bytes : 8);
     if (rc) return rc;
     if (bytes) CU(cudaMemcpyAsync(ctx->d_io[slot], src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -697,6 +780,8 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_bounce, CLR_BOUNCE_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_bounce, CLR_BOUNCE_BYTES);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state2, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS);
@@ -726,6 +811,8 @@ void clr_destroy(clr_ctx* ctx) {
     cudaFree(ctx->d_keepC);
     cudaFree(ctx->d_keepG);
     cudaFree(ctx->d_err);
+    cudaFreeHost(ctx->h_bounce);
+    cudaFree(ctx->d_bounce);
     cudaFree(ctx->d_state2);
     cudaFree(ctx->d_live);
     cudaFreeHost(ctx->h_live);
@@ -863,6 +950,7 @@ int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net_c, int32_t n, const i
     int rc = compile_net(ctx, net, pp, n, &c);
     if (rc) return rc;
     const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    ctx->bounce_open = !dev_io; ctx->bounce_used = ctx->bounce_flushed = 0;
     const void *dc, *dr;
     if ((rc = stage_in(ctx, 0, centers, sizeof(double) * tab, dev_io, &dc))) return rc;
     if ((rc = stage_in(ctx, 1, radii, sizeof(double) * tab, dev_io, &dr))) return rc;
@@ -898,6 +986,7 @@ int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net_c, int32_t n, int64
     DeepzInput in{};
     in.kind = 1; in.n = n; in.N = N;
     int p0max = 0;
+    ctx->bounce_open = !dev_io; ctx->bounce_used = ctx->bounce_flushed = 0;
     if (N > 0) {
         const void *dC, *dO, *dG;
         if (dev_io) {
@@ -1239,6 +1328,7 @@ int32_t clr_forward_points(clr_ctx* ctx, const clr_net* net_c, const clr_prepost
     const int m = c->host.m_out;
     const void* dX;
     double* dU = U;
+    ctx->bounce_open = false;
     if ((rc = stage_in(ctx, 0, X, sizeof(double) * (size_t)nx * N, dev_io, &dX))) return rc;
     if (!dev_io) {
         if ((rc = ensure(ctx, &ctx->d_io[4], &ctx->io_bytes[4], sizeof(double) * (size_t)m * N))) return rc;
@@ -1291,6 +1381,7 @@ static int32_t rollout_impl(clr_ctx* ctx, const clr_net* net_c, const clr_prepos
     A.substeps = substeps; A.pow_mode = pow_mode; A.log_cap = log_cap; A.error = ctx->d_err;
     CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
     const void *dx0, *dWd = nullptr;
+    ctx->bounce_open = false;
     if ((rc = stage_in(ctx, 0, x0, sizeof(double) * (size_t)ns * N, dev_io, &dx0))) return rc;
     if (nd > 0 && (rc = stage_in(ctx, 1, Wd, sizeof(double) * nd * cells, dev_io, &dWd))) return rc;
     A.x0 = (const double*)dx0; A.Wd = (const double*)dWd;

@@ -783,6 +783,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 }
                 // per cell (dealt to the warps, lanes over columns / rows): the position table and the list of the
                 // generators just appended (cell, row, column in the layout after the next product)
+                DZ_T(7);
                 const bool listItems = nIt <= DZ_ITEMS_MAX;
                 for (int ci = warp; ci < keep; ci += nWarps) {
                     const int src = ci & 31;

@@ -43,6 +43,13 @@ __device__ __forceinline__ double ro_act(int act, double s) {
     }
 }
 
+// max(s, 0) without FP64 instructions: clears every bit when the sign bit is set (-0.0 -> +0.0, like s > 0 ? s : 0)
+__device__ __forceinline__ double ro_relu_bits(double s) {
+    const int hi = __double2hiint(s), lo = __double2loint(s);
+    const int keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, lo & keep);
+}
+
 // Evaluate the network on one point.  Layers are processed in pairs: neuron i of layer l is computed
 // from the stored input vector and immediately streamed into the accumulators of layer l+1, so
 // only every other activation vector is materialised.  Summation order = ControllerFormats'
@@ -615,7 +622,7 @@ __device__ __forceinline__ void ro_mlp_small_blocked(const PointNet& net, const 
 #pragma unroll
                     for (int k = 0; k < NI / 2; k++) { s = fma(wv[k].x, va[r][2 * k], s); s = fma(wv[k].y, va[r][2 * k + 1], s); }
                     s += b1;
-                    const double h = relu ? 0.5 * (s + fabs(s)) : ro_act(a1, s);   // exact max(s, 0) in two FP64 instructions
+                    const double h = relu ? ro_relu_bits(s) : ro_act(a1, s);       // max(s, 0) on the integer pipe: the FP64 pipe is the limiter
 #pragma unroll
                     for (int o = 0; o < NO / 2; o++) { vb[r][2 * o] = fma(vv[o].x, h, vb[r][2 * o]); vb[r][2 * o + 1] = fma(vv[o].y, h, vb[r][2 * o + 1]); }
                 }

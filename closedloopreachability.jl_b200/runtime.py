@@ -294,6 +294,10 @@ class Context:
             self._check(self.L.clr_deepz_fetch_reduced(self.h, int(order), _ptr(c), _ptr(G), 0))
         return {"c": c, "G": G}
 
+    def fetch_reduced_dev(self, order, d_c, d_G):
+        """Same with device-resident outputs (CLR_FLAG_DEVICE_IO): d_c (N, m), d_G (N, m*order, m)."""
+        self._check(self.L.clr_deepz_fetch_reduced(self.h, int(order), _ptr(d_c), _ptr(d_G), FLAG_DEVICE_IO))
+
     # device-resident variant: every data pointer is a device pointer / torch CUDA tensor
     def deepz_boxgrid_dev(self, dnet, n, d_partition_host, d_centers, d_radii, cell_begin, cell_count, pp: PrePostArg,
                           d_lo, d_hi, d_hull_lo=None, d_hull_hi=None, stats=None, keep_cap=0):

@@ -15,7 +15,7 @@ cc = torch.from_numpy(np.concatenate(grid.centers)).to(dev); rr = torch.from_num
 lo = torch.empty((cells, 1), dtype=torch.float64, device=dev); hi = torch.empty_like(lo)
 pp = runtime.PrePostArg(None, None)
 ctx.set_profiling(True)
-names = ["input", "product", "appended+sync1", "relax+sync2", "layout+sync3", "output", "fetch", "other"]
+names = ["input", "product", "appended+sync1", "relax+sync2", "layout+sync3", "output", "fetch", "layout-scan"]
 for T in [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["0"])]:
     ctx.set_tile_cells(T)
     for _ in range(2):
