@@ -634,6 +634,8 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     sp.cap = (int)((smem_total - meta) / 8);
     sp.tile_cells = ctx->tile_cells;
     sp.inplace = c->inplace;
+    for (int l = 0; l < D.L; l++)      // every sigmoid / tanh neuron appends a generator (unless its bounds coincide)
+        if (D.layer[l].act == CLR_ACT_SIGMOID || D.layer[l].act == CLR_ACT_TANH) sp.grow_cols += D.layer[l].m;
     sp.retry_list = ctx->d_retry;
     sp.big_list = ctx->d_big;
     sp.workspace = nullptr;
@@ -651,9 +653,9 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
         if (fast_bytes)
             CU(cudaMemcpyAsync(ctx->h_bounce + fast_off, ctx->d_bounce + fast_off, fast_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         fast_done = ctx->h_state->n_retry == 0 && ctx->h_state->n_big == 0;
-        if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     }
     if (!fast || ctx->h_state->n_retry > 0) {
         if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 8, c->dev, in, out, sp))) return rc;

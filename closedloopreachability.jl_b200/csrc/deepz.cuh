@@ -323,7 +323,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         int t0 = sp.tile_cells;
         if (t0 <= 0) {
             int guessCols = in.kind == 0 ? in.n + 1 : 8;
-            t0 = (sp.cap / (inplace ? 1 : 2)) / ((guessCols * 2 + 8) * P);
+            t0 = (sp.cap / (inplace ? 1 : 2)) / ((guessCols * 2 + 8 + sp.grow_cols) * P);
             if (sp.pass != 0) t0 = max(1, t0 / 4);
             unsigned long long fair = (total_units + 2ull * gridDim.x - 1) / (2ull * gridDim.x);
             if ((unsigned long long)t0 > fair) t0 = (int)(fair < 1 ? 1 : fair);

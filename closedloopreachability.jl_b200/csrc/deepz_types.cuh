@@ -35,6 +35,7 @@ struct DeepzSched {
     int tile_cells;           // fixed tile size (0 = adaptive)
     int cap;                  // doubles of column store (+ staging) per CTA
     int inplace;              // 1: layer products run in place (every warp owns at most one row block)
+    int grow_cols;            // generators every cell is known to gain (sigmoid / tanh layers append one per neuron)
     long long* retry_list;
     long long* big_list;
     double* workspace;        // pass 2: gridDim.x * cap doubles
