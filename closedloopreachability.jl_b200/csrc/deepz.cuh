@@ -383,7 +383,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             S.cellId[tid] = sp.pass == 0 ? idx : (sp.pass == 1 ? sp.retry_list[idx] : sp.big_list[idx]);
             if (STATS) S.cellNear[tid] = 0;
         }
-        for (int i = tid; i < nCells * CLR_MASK_WORDS; i += NT) (&S.mask[0][0][0])[i] = 0;
+        for (int i = tid; i < nCells * DZ_MASK_STRIDE; i += NT) (&S.mask[0][0][0])[i] = 0;
         if (needDead) for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) { S.deadMask[0][i] = 0; S.deadMask[1][i] = 0; }
         __syncthreads();
 
@@ -522,8 +522,8 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             const DevLayer& Ly = S.layers[l];
             const int* offNxt = S.colOff[flip ^ 1];
             const unsigned short* wCur = S.wUsed[flip];
-            const unsigned (*pend)[CLR_MASK_WORDS] = S.mask[flip];
-            unsigned (*fresh)[CLR_MASK_WORDS] = S.mask[flip ^ 1];
+            const unsigned (*pend)[DZ_MASK_STRIDE] = S.mask[flip];
+            unsigned (*fresh)[DZ_MASK_STRIDE] = S.mask[flip ^ 1];
             if (STATS && Ly.net_layer >= 0 && tid < nCells) {
                 // generators entering this layer, as the reference counts them
                 const int cb = S.colOff[flip][tid], w = wCur[tid];
@@ -600,7 +600,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     }
                 }
             }
-            for (int i = tid; i < nCells * CLR_MASK_WORDS; i += NT) (&fresh[0][0])[i] = 0;
+            for (int i = tid; i < nCells * DZ_MASK_STRIDE; i += NT) (&fresh[0][0])[i] = 0;
             if (tid == 0) S.kActNew = 0;
             // weights of the next layer (or of the first layer for the next tile) while the relaxation runs
             dz_load_a<KSREG>(S.layers[l + 1 < L ? l + 1 : 0], warp, lane, nWarps, a);

@@ -41,6 +41,7 @@ struct DeepzSched {
     double* workspace;        // pass 2: gridDim.x * cap doubles
 };
 
+#define DZ_MASK_STRIDE (CLR_MASK_WORDS + 1)   // odd row stride: the lanes of a warp read one word of 32 cells without bank conflicts
 #define DZ_ITEMS_MAX 384   // pending generators listed per tile (more: the slow walk over the masks)
 
 struct DeepzSmem {
@@ -57,7 +58,7 @@ struct DeepzSmem {
     int nItems;                                    // pending generators of the tile listed in item*
     unsigned short itemCol[DZ_ITEMS_MAX], itemCell[DZ_ITEMS_MAX], itemRow[DZ_ITEMS_MAX];
     long long cellId[CLR_TILE_CELLS_MAX];
-    unsigned mask[2][CLR_TILE_CELLS_MAX][CLR_MASK_WORDS];   // rows whose relaxation appended a generator: [pending | being written]
+    unsigned mask[2][CLR_TILE_CELLS_MAX][DZ_MASK_STRIDE];   // rows whose relaxation appended a generator: [pending | being written]
     unsigned short colPos[CLR_NCOL_MAX];      // column of the current layout -> column of the next one (0x8000: centre, 0xFFFF: unused)
     unsigned deadMask[2][CLR_NCOL_MAX / 32];  // generators the reference's remove_zero_columns has dropped
     double hlo[CLR_HULL_MAX], hhi[CLR_HULL_MAX];
