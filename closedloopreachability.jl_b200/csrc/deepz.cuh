@@ -127,10 +127,15 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
         const int bp = min(mp.nParts, NB), gp = max(1, mp.nParts / bp);
         const int myB = mp.part % bp, myG = mp.part / bp;
         const bool partOk = mp.part < bp * gp;
-        unsigned blkMask = 0;
-        for (int j = 0; j < NB; j++) if ((j % bp) == myB) blkMask |= 1u << j;
+        unsigned blkMask = 0;     // column blocks j of a group with j % bp == myB (bp divides NB or is NB itself in all common maps)
+        if (bp == 1) blkMask = (1u << NB) - 1u;
+        else if (bp == NB) blkMask = 1u << myB;
+        else if (bp == 2) { for (int j = 0; j < NB; j += 2) blkMask |= 1u << (j + myB); }
+        else { for (int j = 0; j < NB; j++) if ((j % bp) == myB) blkMask |= 1u << j; }
+        int cgm = gp == 1 ? 0 : (CG - 1) % gp;      // cg % gp, kept incrementally
         for (int cg = CG - 1; cg >= 0; cg--) {
-            const bool mine = active && partOk && (gp == 1 || (cg % gp) == myG);
+            const bool mine = active && partOk && (gp == 1 || cgm == myG);
+            if (gp != 1) cgm = cgm == 0 ? gp - 1 : cgm - 1;
             double d[NB][2];
 #pragma unroll
             for (int j = 0; j < NB; j++) { d[j][0] = 0.0; d[j][1] = 0.0; }
