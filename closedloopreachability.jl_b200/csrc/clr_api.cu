@@ -461,14 +461,21 @@ int worst_cols(const DevNet& D, int p0) {
 
 namespace {
 
-int launch_deepz(clr_ctx* ctx, bool global, bool stats, int ksreg, int grid, int threads, size_t smem,
-                 const DevNet* net, const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
+int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int grid, int threads, size_t smem,
+                 const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
     cudaError_t e;
+    const int ksreg = c->ksreg;
+    const DevNet* net = c->dev;
+    bool full = false;     // sigmoid / tanh layers or streamed products: the full instantiation
+    for (int l = 0; l < c->host.L; l++) {
+        const DevLayer& d = c->host.layer[l];
+        full = full || d.act == CLR_ACT_SIGMOID || d.act == CLR_ACT_TANH || d.ksteps > ksreg;
+    }
     switch (ksreg) {   // one translation unit per KSREG (deepz_ks*.cu), so that the instantiations compile in parallel
-        case 8: e = launch_deepz_ks8(global, stats, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        case 16: e = launch_deepz_ks16(global, stats, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        case 25: e = launch_deepz_ks25(global, stats, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        default: e = launch_deepz_ks32(global, stats, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 8: e = launch_deepz_ks8(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 16: e = launch_deepz_ks16(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 25: e = launch_deepz_ks25(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        default: e = launch_deepz_ks32(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
     }
     if (e != cudaSuccess) return fail(ctx, CLR_ERR_CUDA, "DeepZ kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
@@ -514,8 +521,8 @@ int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& 
     sp.big_list = ctx->d_big;             // overflowing cells are simply not sampled (the list is reset by the real run)
     DevCallState* saved = ctx->d_state;
     ctx->d_state = ctx->d_state2;
-    int rc = launch_deepz(ctx, false, false, c->ksreg, (int)std::min<long long>(ctx->sms, S), DZ_THREADS, meta + (size_t)sp.cap * 8,
-                          c->dev, in, out, sp);
+    int rc = launch_deepz(ctx, false, false, c, (int)std::min<long long>(ctx->sms, S), DZ_THREADS, meta + (size_t)sp.cap * 8,
+                          in, out, sp);
     ctx->d_state = saved;
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->h_live, ctx->d_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS, cudaMemcpyDeviceToHost, ctx->stream));
@@ -644,7 +651,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     sp.pass = 0;
     ctx->pass_ms[0] = ctx->pass_ms[1] = ctx->pass_ms[2] = 0.f;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 8, c->dev, in, out, sp))) return rc;
+    if ((rc = launch_deepz(ctx, false, want_stats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
     bool fast_done = false;
@@ -658,7 +665,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         fast_done = ctx->h_state->n_retry == 0 && ctx->h_state->n_big == 0;
     }
     if (!fast || ctx->h_state->n_retry > 0) {
-        if ((rc = launch_deepz(ctx, false, want_stats, c->ksreg, grid, threads, meta + (size_t)sp.cap * 8, c->dev, in, out, sp))) return rc;
+        if ((rc = launch_deepz(ctx, false, want_stats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         // how many cells did not fit in shared memory at all?
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -681,7 +688,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, need))) return rc;
         sg.workspace = ctx->d_ws;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        if ((rc = launch_deepz(ctx, true, want_stats, c->ksreg, gridg, threads, dz_meta_bytes(want_stats), c->dev, in, out, sg))) return rc;
+        if ((rc = launch_deepz(ctx, true, want_stats, c, gridg, threads, dz_meta_bytes(want_stats), in, out, sg))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
