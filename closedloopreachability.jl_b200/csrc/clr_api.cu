@@ -471,6 +471,7 @@ int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int g
         const DevLayer& d = c->host.layer[l];
         full = full || d.act == CLR_ACT_SIGMOID || d.act == CLR_ACT_TANH || d.ksteps > ksreg;
     }
+    full = full || !c->inplace;                 // two-buffer products (a layer wider than 128 neurons)
     switch (ksreg) {   // one translation unit per KSREG (deepz_ks*.cu), so that the instantiations compile in parallel
         case 8: e = launch_deepz_ks8(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
         case 16: e = launch_deepz_ks16(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
@@ -634,7 +635,9 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     CU(cudaMemsetAsync(ctx->d_state, 0, sizeof(DevCallState), ctx->stream));
 
     const int threads = DZ_THREADS;
-    const size_t meta = dz_meta_bytes(want_stats);
+    // kept zonotopes need the zero-generator bookkeeping, which only the STATS instantiations carry
+    const bool kstats = want_stats || keep_cap > 0;
+    const size_t meta = dz_meta_bytes(kstats);
     const size_t smem_total = (size_t)ctx->smem_optin;
     if (smem_total < meta + 8 * 1024) return fail(ctx, CLR_ERR_CUDA, "device has too little shared memory");
     DeepzSched sp{};
@@ -651,7 +654,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     sp.pass = 0;
     ctx->pass_ms[0] = ctx->pass_ms[1] = ctx->pass_ms[2] = 0.f;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if ((rc = launch_deepz(ctx, false, want_stats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
+    if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
     bool fast_done = false;
@@ -665,7 +668,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         fast_done = ctx->h_state->n_retry == 0 && ctx->h_state->n_big == 0;
     }
     if (!fast || ctx->h_state->n_retry > 0) {
-        if ((rc = launch_deepz(ctx, false, want_stats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
+        if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         // how many cells did not fit in shared memory at all?
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -688,7 +691,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, need))) return rc;
         sg.workspace = ctx->d_ws;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        if ((rc = launch_deepz(ctx, true, want_stats, c, gridg, threads, dz_meta_bytes(want_stats), in, out, sg))) return rc;
+        if ((rc = launch_deepz(ctx, true, kstats, c, gridg, threads, dz_meta_bytes(kstats), in, out, sg))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));

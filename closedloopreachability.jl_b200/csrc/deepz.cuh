@@ -299,9 +299,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
     const int P = net->max_pitch;                 // one column pitch for the whole network
     const int mOut = net->m_out;
     const int n = in.n;
-    const bool inplace = sp.inplace != 0;
+    const bool inplace = FULL ? sp.inplace != 0 : true;      // lean variant: every warp owns at most one row block
     const bool useHull = out.hull_lo != nullptr && mOut <= CLR_HULL_MAX;
-    const bool needDead = STATS || out.keep_cap > 0;
+    const bool needDead = STATS;                  // kept zonotopes are only written by the STATS instantiations
     const int stageW = max(clr_pad4(net->max_rows), 2 * n);   // doubles of staging per cell
 
     // ---- one-time setup: layer descriptors to smem, accumulators, the first tile ------------------
@@ -841,7 +841,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[flip][tid][ww]);
                     rank0[tid] = k;
                     if (STATS) atomicMax(&S.sMaxP, k + u);
-                    if (out.keep_cap > 0) {
+                    if (STATS && out.keep_cap > 0) {
                         out.keepN[S.cellId[tid]] = k + u;
                         if (k + u > out.keep_cap) atomicCAS(&st->error, 0, (int)CLR_ERR_CAPACITY);
                     }
@@ -872,7 +872,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     if (useHull) { atomicMinD(&S.hlo[r], lo); atomicMaxD(&S.hhi[r], hi); }
                     else { atomicMinD(&out.hull_lo[r], lo); atomicMaxD(&out.hull_hi[r], hi); }
                 }
-                if (out.keep_cap > 0) {
+                if (STATS && out.keep_cap > 0) {
                     out.keepC[cell * mOut + r] = c;
                     double* g = out.keepG + (size_t)cell * out.keep_cap * mOut + r;
                     for (int j = 1; j < w; j++) {
