@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > $O/f_bench_ref.json 2>> 
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/f_launches.csv python bench.py --steps 2 --warmup 1 > $O/f_ncu_launch.log 2>&1
 T=/tmp/ncu_reports; mkdir -p $T
 ncu --set full --clock-control none --import-source on -k regex:deepz_kernel -c 6 -o $T/deepz python bench.py --steps 1 --warmup 1 --no-secondary --no-cpu-baseline > $O/f_ncu_deepz.log 2>&1
-python profiles/ncu_summary.py $T/deepz.ncu-rep deepz_kernel "ncu --set full --clock-control none, main-pass deepz_kernel launch of bench.py (10^6 cells, stable regime)" longest "<25, 0, 0>" > $O/f_ncu_deepz.json
+python profiles/ncu_summary.py $T/deepz.ncu-rep deepz_kernel "ncu --set full --clock-control none, main-pass deepz_kernel launch of bench.py (10^6 cells, stable regime)" longest "<25, 0, 0, 0>" > $O/f_ncu_deepz.json
 ncu -i $T/deepz.ncu-rep --page raw --csv --metrics gpu__time_duration.sum > $O/f_ncu_deepz_launches.csv
 ncu -i $T/deepz.ncu-rep --page source --csv --print-source cuda,sass --launch-skip 4 --launch-count 1 > $T/deepz_src.csv
 python profiles/ncu_lines.py $T/deepz_src.csv 60 > $O/f_ncu_deepz_lines.txt
