@@ -186,6 +186,9 @@ def run_ours(args):
     rank, local, world = dist_env()
     import torch.distributed as dist
     if world > 1:
+        # NCCL logs (e.g. its version banner when NCCL_DEBUG is set on the box) go to stdout by default: keep stdout for
+        # the ONE JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
