@@ -19,7 +19,7 @@ SYMBOLS = [
     "clr_device_alloc", "clr_device_free", "clr_memcpy_h2d", "clr_memcpy_d2h", "clr_set_tile_cells",
     "clr_set_profiling", "clr_last_pass_info", "clr_set_reorder",
     "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_zonotopes",
-    "clr_deepz_fetch_zonotopes", "clr_deepz_fetch_reduced", "clr_forward_points", "clr_rollout",
+    "clr_deepz_fetch_zonotopes", "clr_deepz_fetch_reduced", "clr_project_oa", "clr_forward_points", "clr_rollout",
     "clr_plant_compile", "clr_plant_free", "clr_rollout_plant",
 ]
 
@@ -89,6 +89,8 @@ def lib():
     L.clr_deepz_fetch_zonotopes.restype = i32
     L.clr_deepz_fetch_reduced.argtypes = [vp, i32, vp, vp, i32]
     L.clr_deepz_fetch_reduced.restype = i32
+    L.clr_project_oa.argtypes = [vp, i32, i32, i32, vp, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, i32]
+    L.clr_project_oa.restype = i32
     L.clr_forward_points.argtypes = [vp, vp, vp, i32, i64, vp, vp, i32]
     L.clr_forward_points.restype = i32
     L.clr_rollout.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i32, vp, vp, dbl, dbl, dbl, i32, dbl, dbl,

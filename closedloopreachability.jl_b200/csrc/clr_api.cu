@@ -18,6 +18,7 @@
 #include "deepz_launch.h"
 #include "rollout.cuh"
 #include "reduce.cuh"
+#include "project.cuh"
 
 #define CLR_BOUNCE_BYTES (1u << 20)  // pinned bounce buffer of the small-call path
 #define CLR_BOUNCE_IN_MAX (256u << 10)
@@ -1084,6 +1085,76 @@ int32_t clr_deepz_fetch_reduced(clr_ctx* ctx, int32_t order, double* out_c, doub
     if (err)
         return fail(ctx, CLR_ERR_DIM, "order-%d reduction needs at least %d generators per zonotope (the reference's reduce_order "
                     "indexes past the end there)", order, (int)m * (order - 1));
+    return 0;
+}
+
+int32_t clr_project_oa(clr_ctx* ctx, int32_t n, int32_t order_t, int32_t n_monomials, const int32_t* exponents, int64_t N,
+                       const double* coeffs, const double* rem, const double* dt, const int32_t* vars, int32_t n_keep,
+                       int32_t remove_zero_generators, double* out_c, double* out_G, int32_t* out_ncols, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (n < 1 || n > 64 || order_t < 0 || n_monomials < 1 || N < 0 || n_keep < 1 || n_keep > n)
+        return fail(ctx, CLR_ERR_DIM, "clr_project_oa: bad dimensions (n = %d, order_t = %d, monomials = %d, kept = %d)", n, order_t,
+                    n_monomials, n_keep);
+    if (!exponents || !vars || (N > 0 && (!coeffs || !rem || !dt || !out_c || !out_G || !out_ncols)))
+        return fail(ctx, CLR_ERR_ARG, "clr_project_oa: NULL argument");
+    for (int k = 0; k < n_keep; k++)
+        if (vars[k] < 0 || vars[k] >= n) return fail(ctx, CLR_ERR_DIM, "clr_project_oa: variable %d outside 0..%d", vars[k], n - 1);
+    if (N == 0) return 0;
+    CU(cudaSetDevice(ctx->device));
+    ctx->bounce_open = false;
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    // classify the monomials once: constant / linear in variable j / nonlinear (all exponents even or not)
+    const int M = n_monomials;
+    std::vector<int> meta((size_t)M + n_keep);
+    int n_const = 0;
+    for (int m = 0; m < M; m++) {
+        int deg = 0, lin = -1; bool even = true;
+        for (int j = 0; j < n; j++) {
+            const int e = exponents[(size_t)m * n + j];
+            if (e < 0) return fail(ctx, CLR_ERR_ARG, "clr_project_oa: negative exponent");
+            deg += e; if (e == 1) lin = j; if (e & 1) even = false;
+        }
+        meta[(size_t)m] = deg == 0 ? -1 : (deg == 1 ? lin : (even ? -2 : -3));
+        n_const += deg == 0;
+    }
+    if (n_const != 1) return fail(ctx, CLR_ERR_ARG, "clr_project_oa: the exponent table needs exactly one constant monomial (has %d)", n_const);
+    for (int k = 0; k < n_keep; k++) meta[(size_t)M + k] = vars[k];
+    const size_t bcoef = sizeof(double) * (size_t)N * n * (order_t + 1) * M, brem = sizeof(double) * (size_t)N * n * 2;
+    const size_t bC = sizeof(double) * (size_t)N * n_keep, bG = sizeof(double) * (size_t)N * 2 * n * n_keep;
+    const size_t bscr = sizeof(double) * (size_t)N * n_keep * (n + 2);
+    int rc;
+    const void *dcoef, *drem, *ddt, *dmeta;
+    if ((rc = stage_in(ctx, 0, coeffs, bcoef, dev_io, &dcoef))) return rc;
+    if ((rc = stage_in(ctx, 1, rem, brem, dev_io, &drem))) return rc;
+    if ((rc = stage_in(ctx, 2, dt, sizeof(double) * (size_t)N, dev_io, &ddt))) return rc;
+    if ((rc = stage_in(ctx, 3, meta.data(), sizeof(int) * meta.size(), false, &dmeta))) return rc;
+    ProjArgs A;
+    A.N = (long long)N; A.n = n; A.KT = order_t + 1; A.M = M; A.nkeep = n_keep; A.remove_zero = remove_zero_generators != 0;
+    A.cls = (const int*)dmeta; A.vars = (const int*)dmeta + M;
+    A.coeffs = (const double*)dcoef; A.rem = (const double*)drem; A.dt = (const double*)ddt;
+    if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, bscr))) return rc;
+    A.scratch = ctx->d_ws;
+    CU(cudaMemsetAsync(A.scratch, 0, bscr, ctx->stream));
+    if (dev_io) { A.outC = out_c; A.outG = out_G; A.outN = out_ncols; }
+    else {
+        if ((rc = ensure(ctx, &ctx->d_io[5], &ctx->io_bytes[5], bC))) return rc;
+        if ((rc = ensure(ctx, &ctx->d_io[6], &ctx->io_bytes[6], bG))) return rc;
+        if ((rc = ensure(ctx, &ctx->d_io[7], &ctx->io_bytes[7], sizeof(int) * (size_t)N))) return rc;
+        A.outC = (double*)ctx->d_io[5]; A.outG = (double*)ctx->d_io[6]; A.outN = (int*)ctx->d_io[7];
+    }
+    const long long units = (long long)N * n_keep;
+    const int grid1 = (int)std::max<long long>(1, std::min<long long>((units + PJ_WARPS - 1) / PJ_WARPS, (long long)ctx->sms * 16));
+    project_eval_kernel<<<grid1, PJ_WARPS * 32, 0, ctx->stream>>>(A);
+    CU(cudaGetLastError());
+    project_pack_kernel<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    if (!dev_io) {
+        CU(cudaMemcpyAsync(out_c, A.outC, bC, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_G, A.outG, bG, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_ncols, A.outN, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     return 0;
 }
 

@@ -294,6 +294,37 @@ class Context:
             self._check(self.L.clr_deepz_fetch_reduced(self.h, int(order), _ptr(c), _ptr(G), 0))
         return {"c": c, "G": G}
 
+    def project_oa(self, exps, coeffs, rem, dt, vars_keep, remove_zero_generators=True):
+        """Batched ``_project_oa(R::AbstractTaylorModelReachSet, vars, t)`` (reference src/setops.jl:9-12) for the N reach-sets
+        that end the chains of a control period (src/solve.jl:181-184).
+
+        exps (M, n): exponents of the monomials in TaylorSeries' coefficient order; coeffs (N, n, order_t + 1, M): time
+        coefficient k of component v, as a polynomial in the n normalised space variables; rem (N, n, 2): remainder
+        intervals; dt (N,): evaluation time minus the expansion point; vars_keep: 0-based components kept.
+        -> c (N, n_keep), G (N, 2n, n_keep) (row j = generator j), ncols (N,): ready for ``deepz_zonotopes``."""
+        exps = np.ascontiguousarray(exps, dtype=np.int32)
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        if exps.ndim != 2 or coeffs.ndim != 4 or coeffs.shape[1] != exps.shape[1] or coeffs.shape[3] != exps.shape[0]:
+            raise ClrArgumentError(ERR_DIM, "coeffs must be (N, n, order_t + 1, M) with exps (M, n)")
+        N, n, KT, M = coeffs.shape
+        rem = np.ascontiguousarray(rem, dtype=np.float64)
+        dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (N,)))
+        if rem.shape != (N, n, 2):
+            raise ClrArgumentError(ERR_DIM, "rem must be (N, n, 2)")
+        vk = np.ascontiguousarray(vars_keep, dtype=np.int32)
+        c = np.zeros((N, len(vk))); G = np.zeros((N, 2 * n, len(vk))); nc = np.zeros(N, dtype=np.int32)
+        self._check(self.L.clr_project_oa(self.h, n, KT - 1, M, _ptr(exps), N, _ptr(coeffs), _ptr(rem), _ptr(dt), _ptr(vk),
+                                          len(vk), int(bool(remove_zero_generators)), _ptr(c), _ptr(G), _ptr(nc), 0))
+        return {"c": c, "G": G, "ncols": nc}
+
+    def project_oa_dev(self, n, order_t, exps, N, d_coeffs, d_rem, d_dt, vars_keep, remove_zero_generators, d_c, d_G, d_ncols):
+        """Same with device-resident arrays (CLR_FLAG_DEVICE_IO); exps / vars_keep stay host arrays."""
+        exps = np.ascontiguousarray(exps, dtype=np.int32)
+        vk = np.ascontiguousarray(vars_keep, dtype=np.int32)
+        self._check(self.L.clr_project_oa(self.h, int(n), int(order_t), exps.shape[0], _ptr(exps), int(N), _ptr(d_coeffs), _ptr(d_rem),
+                                          _ptr(d_dt), _ptr(vk), len(vk), int(bool(remove_zero_generators)), _ptr(d_c), _ptr(d_G),
+                                          _ptr(d_ncols), FLAG_DEVICE_IO))
+
     def fetch_reduced_dev(self, order, d_c, d_G):
         """Same with device-resident outputs (CLR_FLAG_DEVICE_IO): d_c (N, m), d_G (N, m*order, m)."""
         self._check(self.L.clr_deepz_fetch_reduced(self.h, int(order), _ptr(d_c), _ptr(d_G), FLAG_DEVICE_IO))

@@ -25,6 +25,8 @@
  *   clr_deepz_fetch_zonotopes the output set U of controller_forward (src/solve.jl:213) when the caller
  *                             needs more than its box (TaylorModelReconstructor(box=false), src/setops.jl:84-107)
  *   clr_deepz_fetch_reduced   _reduce_order(Z0, 2; force_reduction=true) of the same reconstructor, src/setops.jl:84-86
+ *   clr_project_oa            _project_oa(R::AbstractTaylorModelReachSet, vars, t), src/setops.jl:9-12, for all chains of a
+ *                             control period at once (src/solve.jl:181-184)
  *   clr_forward_points        forward(x, network) + pre/post-processing, src/simulate.jl:101-106
  *   clr_rollout               the period loop of simulate (src/simulate.jl:98-140) incl. _solve_ensemble
  *                             (ext/ClosedLoopReachabilityOrdinaryDiffEqExt.jl:28-45: Tsit5 ensemble)
@@ -175,6 +177,23 @@ int32_t clr_deepz_fetch_zonotopes(clr_ctx* ctx, int32_t* out_ncols, double* out_
  * (CLR_ERR_DIM; the reference throws there).  flags: CLR_FLAG_DEVICE_IO makes out_c / out_G device pointers.
  */
 int32_t clr_deepz_fetch_reduced(clr_ctx* ctx, int32_t order, double* out_c, double* out_G, int32_t flags);
+
+/*
+ * Batched _project_oa of Taylor-model reach-sets (src/setops.jl:9-12), the step that produces the cells of a control
+ * period k > 1 (src/solve.jl:181-184):  project(set(overapproximate(R, Zonotope, t)), vars)  for N reach-sets at once.
+ * Every reach-set has n components; component v is a polynomial in time (order_t + 1 coefficients) whose coefficients
+ * are polynomials in the n normalised space variables (n_monomials monomials, exponents[m*n + j] = exponent of variable
+ * j in monomial m -- TaylorSeries' coefficient order, i.e. coeff_table, flattened over the degrees), plus an interval
+ * remainder.  coeffs: n_monomials x (order_t+1) x n x N (monomial index fastest), rem: 2 x n x N (lo, hi),
+ * dt: N evaluation times relative to the expansion point of the time polynomial, vars: n_keep 0-based components kept.
+ * Output zonotopes: out_c (n_keep x N), out_G (n_keep x 2n x N: generator j of reach-set i at out_G + (i*2n + j)*n_keep,
+ * columns [linear terms | remainder radii]), out_ncols (N).  With remove_zero_generators != 0 all-zero columns are
+ * dropped (the keyword of the reference); parallel columns are NOT merged (LazySets' remove_redundant_generators):
+ * the result is the same set.  The arrays are device pointers with CLR_FLAG_DEVICE_IO (exponents / vars stay host).
+ */
+int32_t clr_project_oa(clr_ctx* ctx, int32_t n, int32_t order_t, int32_t n_monomials, const int32_t* exponents, int64_t N,
+                       const double* coeffs, const double* rem, const double* dt, const int32_t* vars, int32_t n_keep,
+                       int32_t remove_zero_generators, double* out_c, double* out_G, int32_t* out_ncols, int32_t flags);
 
 /* ---- pointwise controller -------------------------------------------------------------------- */
 /* X: nx x N, U: m_out x N */

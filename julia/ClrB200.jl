@@ -123,6 +123,27 @@ function reduced_controls(ctx::Context, m::Integer, N::Integer; order::Integer=2
 end
 
 """
+Batched `_project_oa(R::AbstractTaylorModelReachSet, vars, t)` (src/setops.jl:9-12) for the reach-sets `Rs` that end the
+live chains of a control period (src/solve.jl:181-184): one call instead of one `overapproximate(R, Zonotope, t)` +
+`project` per chain.  The Taylor models are flattened on the Julia side: component v of reach-set i is a
+`TaylorModel1{TaylorN{Float64},Float64}`; its time coefficient k contributes `vcat((c.coeffs for c in p[k].coeffs)...)`
+(all homogeneous polynomials, degree 0 first -- TaylorSeries' coefficient order), the exponent table is
+`reduce(hcat, vcat(TaylorSeries.coeff_table...))`, and dt = t - tstart(R).  Returns the centres (n_keep x N), the
+generators (n_keep x 2n x N) and the generator counts: the arguments `clr_deepz_zonotopes` takes for the next period.
+"""
+function project_oa_batch(ctx::Context, exps::Matrix{Int32}, coeffs::Array{Float64,4}, rem::Array{Float64,3}, dt::Vector{Float64},
+                          vars::Vector{Int32}; remove_zero_generators::Bool=true)
+    n, M = size(exps); KT = size(coeffs, 2); N = size(coeffs, 4)          # coeffs: M x KT x n x N, rem: 2 x n x N
+    nk = length(vars)
+    c = Matrix{Float64}(undef, nk, N); G = Array{Float64}(undef, nk, 2n, N); ncols = Vector{Int32}(undef, N)
+    check(ctx, ccall((:clr_project_oa, LIB), Int32,
+                     (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32,
+                      Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32),
+                     ctx.h, n, KT - 1, M, exps, N, coeffs, rem, dt, vars .- Int32(1), nk, remove_zero_generators, c, G, ncols, 0))
+    return c, G, ncols
+end
+
+"""
 `simulate`'s period loop (src/simulate.jl:98-140) for a built-in plant: x0 is n_state x N, Wd n_dist x N x iters
 (drawn on the Julia side in the reference's RNG order: x0 once, then W0 once per period, src/simulate.jl:89, :111).
 """

@@ -476,3 +476,90 @@ def reduce_order_gir05(c, G, r=2):
             acc += abs(float(G[i, j]))
         d[i] = acc
     return c.copy(), np.hstack([G[:, order[:kept]], np.diag(d)])
+
+
+# --------------------------------------------------------------------------------------
+# _project_oa(R::AbstractTaylorModelReachSet, vars, t)            (src/setops.jl:9-12) [UPSTREAM-RECALL]
+#   = project(set(overapproximate(R, Zonotope, t)), vars; remove_zero_generators)
+# ReachabilityAnalysis overapproximate(::TaylorModelReachSet, Zonotope, t): evaluate the TaylorModel1 components at
+# t - t0 (TaylorSeries Horner, plain Float64), TaylorModelN over the symmetric box, fp_rpa, then LazySets
+# overapproximate(::Vector{<:TaylorModelN}, Zonotope): constant + linear terms -> centre / generators, the nonlinear
+# terms and the remainder -> an interval whose midpoint moves the centre and whose radius is a generator r_v e_v.
+# Interval additions round outwards exactly (directed rounding via TwoSum); multiplications by 0 / +-1 are exact.
+# LazySets' remove_redundant_generators (merging parallel columns) is not restated: same set, unmerged columns.
+# --------------------------------------------------------------------------------------
+def _two_sum(a: float, b: float):
+    s = a + b
+    bb = s - a
+    return s, (a - (s - bb)) + (b - bb)
+
+
+def _add_dn(a: float, b: float) -> float:
+    """a + b rounded towards -inf (exact directed rounding through the error-free TwoSum)."""
+    s, e = _two_sum(a, b)
+    return math.nextafter(s, -math.inf) if e < 0.0 else s
+
+
+def _add_up(a: float, b: float) -> float:
+    s, e = _two_sum(a, b)
+    return math.nextafter(s, math.inf) if e > 0.0 else s
+
+
+def monomial_table(n: int, order: int):
+    """Exponent table in TaylorSeries' coefficient order: by total degree, and inside a degree the order of
+    TaylorSeries.coeff_table (descending lexicographic: x1^d first).  Shape (M, n)."""
+    out = []
+    for d in range(order + 1):
+        def rec(prefix, left, k):
+            if k == n - 1:
+                out.append(prefix + [left]); return
+            for e in range(left, -1, -1):
+                rec(prefix + [e], left - e, k + 1)
+        rec([], d, 0)
+    return np.array(out, dtype=np.int32)
+
+
+def project_oa_taylor_model(exps, coeffs, rem, dt, vars_keep, remove_zero_generators=True):
+    """One reach-set.  exps (M, n); coeffs (n, KT, M); rem (n, 2); dt scalar; vars_keep 0-based.
+    Returns (c (n_keep,), G (n_keep, p))."""
+    exps = np.asarray(exps); n = exps.shape[1]
+    coeffs = np.asarray(coeffs, dtype=np.float64); rem = np.asarray(rem, dtype=np.float64)
+    KT, M = coeffs.shape[1], coeffs.shape[2]
+    deg = exps.sum(axis=1)
+    c = np.zeros(n); Glin = np.zeros((n, n)); rad = np.zeros(n)
+    for v in range(n):
+        lo = hi = 0.0
+        c0 = 0.0
+        for m in range(M):
+            s = float(coeffs[v, KT - 1, m])
+            for k in range(KT - 2, -1, -1):
+                s = s * float(dt) + float(coeffs[v, k, m])          # TaylorSeries evaluate: suma = suma*dt + a[k]
+            if deg[m] == 0:
+                c0 = s
+            elif deg[m] == 1:
+                Glin[v, int(np.argmax(exps[m]))] = s
+            elif np.all(exps[m] % 2 == 0):                           # s * [0, 1]
+                lo = _add_dn(lo, min(s, 0.0)); hi = _add_up(hi, max(s, 0.0))
+            else:                                                    # s * [-1, 1]
+                lo = _add_dn(lo, -abs(s)); hi = _add_up(hi, abs(s))
+        i0lo, i0hi = _add_dn(c0, float(rem[v, 0])), _add_up(c0, float(rem[v, 1]))
+        c0m = 0.5 * (i0lo + i0hi)                                    # fp_rpa
+        rlo, rhi = _add_dn(i0lo, -c0m), _add_up(i0hi, -c0m)
+        lo, hi = _add_dn(lo, rlo), _add_up(hi, rhi)
+        c[v] = c0m + 0.5 * (lo + hi)
+        rad[v] = 0.5 * _add_up(hi, -lo)
+    G = np.hstack([Glin, np.diag(rad)])
+    vk = list(vars_keep)
+    c, G = c[vk], G[vk, :]                                           # LazySets.project
+    if remove_zero_generators:
+        G = remove_zero_columns(G)
+    return c, G
+
+
+def eval_taylor_model_point(exps, coeffs, dt, xi):
+    """Value of the polynomial part at the normalised point xi (test helper for the soundness property)."""
+    exps = np.asarray(exps); coeffs = np.asarray(coeffs, dtype=np.float64)
+    n, KT, M = coeffs.shape
+    mono = np.prod(np.power(np.asarray(xi, dtype=np.float64)[None, :], exps), axis=1)       # (M,)
+    tpow = float(dt) ** np.arange(KT)
+    return np.einsum("vkm,k,m->v", coeffs, tpow, mono)

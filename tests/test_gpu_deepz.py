@@ -476,3 +476,50 @@ def test_order_reduction_errors(ctx):
         ctx.fetch_reduced(2, 3, 200)                           # needs 597 generators: the reference throws here
     with pytest.raises(Exception):
         ctx.fetch_reduced(2, 3, 0)
+
+
+def test_project_oa_batched(ctx):
+    """_project_oa(R::AbstractTaylorModelReachSet, vars, t) (src/setops.jl:9-12) for a batch of reach-sets: against the
+    NumPy restatement, the enclosure property at full size, and chained into the controller propagation."""
+    from oracle import deepz_np as dz
+    from test_oracle import _random_taylor_models
+    rng = np.random.default_rng(21)
+    N, n, oT, oQ = 64, 6, 8, 3                              # TORA-like: 4 states + disturbance/control variables, TMJets orders
+    exps, coeffs, rem, dt = _random_taylor_models(rng, N, n, oT, oQ)
+    vk = [0, 1, 2, 3]
+    got = ctx.project_oa(exps, coeffs, rem, dt, vk)
+    for i in range(N):
+        c, G = dz.project_oa_taylor_model(exps, coeffs[i], rem[i], dt[i], vk)
+        p = got["ncols"][i]
+        assert p == G.shape[1]
+        scale = max(np.abs(G).max(), np.abs(c).max())
+        np.testing.assert_allclose(got["c"][i], c, rtol=0, atol=1e-12 * scale)
+        np.testing.assert_allclose(got["G"][i, :p].T, G, rtol=0, atol=1e-12 * scale)
+    # zero columns kept on request: always 2 n columns
+    got0 = ctx.project_oa(exps, coeffs, rem, dt, vk, remove_zero_generators=False)
+    assert np.all(got0["ncols"] == 2 * n)
+    np.testing.assert_allclose(np.abs(got0["G"]).sum(axis=1), np.abs(got["G"]).sum(axis=1), rtol=0, atol=1e-12)
+    # enclosure at a larger size: every sampled point of every Taylor model lies in the box of its zonotope
+    N2 = 20000
+    exps, coeffs, rem, dt = _random_taylor_models(rng, N2, n, 4, 2)
+    big = ctx.project_oa(exps, coeffs, rem, dt, vk)
+    rad = np.abs(big["G"]).sum(axis=1)
+    lo, hi = big["c"] - rad, big["c"] + rad
+    tpow = dt[:, None] ** np.arange(5)[None, :]
+    for _ in range(4):
+        xi = rng.uniform(-1, 1, size=(N2, n))
+        mono = np.prod(np.power(xi[:, None, :], exps[None, :, :]), axis=2)            # (N2, M)
+        val = np.einsum("ivkm,ik,im->iv", coeffs, tpow, mono)[:, vk]
+        assert np.all(val + rem[:, vk, 0] >= lo - 1e-12) and np.all(val + rem[:, vk, 1] <= hi + 1e-12)
+    # the zonotopes feed the controller propagation of the next control period (src/solve.jl:183-195)
+    net = load_net("TORA_ReLU")
+    dn = ctx.upload(net)
+    sub = slice(0, 500)
+    nc = big["ncols"][sub]
+    col_off = np.concatenate([[0], np.cumsum(nc)]).astype(np.int64)
+    Gp = np.concatenate([big["G"][i, :nc[k]] for k, i in enumerate(range(500))])
+    out = ctx.deepz_zonotopes(dn, big["c"][sub], col_off, Gp, post=("shift", -10.0))
+    ref = _oracle().deepz_zonotopes(_oracle().Net(net.as_tuples()), big["c"][sub], col_off, Gp, post=("shift", -10.0))
+    _cmp_boxes(out, ref)
+    with pytest.raises(Exception):
+        ctx.project_oa(exps, coeffs, rem, dt, [7])           # variable outside 0..n-1

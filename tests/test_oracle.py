@@ -212,3 +212,47 @@ def test_reduce_order_numpy_vs_c_and_box_invariance(m, order):
             cbind.reduce_order(np.zeros(1, dtype=np.int32), c[:1], G[:1], order)
         else:
             raise IndexError
+
+
+# ---- _project_oa of Taylor-model reach-sets (src/setops.jl:9-12) ----
+def _random_taylor_models(rng, N, n, order_t, order_q, scale=0.1):
+    exps = dz.monomial_table(n, order_q)
+    M = exps.shape[0]
+    deg = exps.sum(axis=1)
+    coeffs = rng.normal(size=(N, n, order_t + 1, M)) * (scale ** deg)[None, None, None, :] / (1.0 + np.arange(order_t + 1))[None, None, :, None]
+    for v in range(n):                                     # time-0 term: identity map of the initial box plus an offset
+        coeffs[:, v, 0, :] = 0.0
+        coeffs[:, v, 0, 0] = rng.normal(size=N)
+        coeffs[:, v, 0, 1 + v] = scale
+    rem = np.sort(rng.normal(size=(N, n, 2)) * 1e-6, axis=2)
+    dt = rng.uniform(0.05, 0.2, size=N)
+    return exps, coeffs, rem, dt
+
+
+def test_project_oa_hand_example():
+    # x(t) = (1 + t) + (0.5 + t) xi1 + 0.25 xi1^2 - 0.125 xi1 xi2 + [-0.01, 0.02];  y(t) = 2 + xi2  (no remainder)
+    exps = dz.monomial_table(2, 2)                         # [0,0],[1,0],[0,1],[2,0],[1,1],[0,2]
+    coeffs = np.zeros((2, 2, 6))
+    coeffs[0, 0] = [1.0, 0.5, 0.0, 0.25, -0.125, 0.0]; coeffs[0, 1] = [1.0, 1.0, 0.0, 0.0, 0.0, 0.0]
+    coeffs[1, 0] = [2.0, 0.0, 1.0, 0.0, 0.0, 0.0]
+    rem = np.array([[-0.01, 0.02], [0.0, 0.0]])
+    c, G = dz.project_oa_taylor_model(exps, coeffs, rem, 0.5, [0, 1])
+    # at t = 0.5: constant 1.5, linear 1.0 xi1; nonlinear range 0.25 [0,1] + 0.125 [-1,1] = [-0.125, 0.375]; with the
+    # remainder [-0.135, 0.395]: centre 1.5 + 0.13, radius 0.265
+    np.testing.assert_allclose(c, [1.63, 2.0], rtol=0, atol=1e-14)
+    assert G.shape == (2, 3)                               # columns: xi1, xi2, remainder of x (y has none: zero column removed)
+    np.testing.assert_allclose(G, [[1.0, 0.0, 0.265], [0.0, 1.0, 0.0]], rtol=0, atol=1e-14)
+    c1, G1 = dz.project_oa_taylor_model(exps, coeffs, rem, 0.5, [1], remove_zero_generators=False)
+    assert G1.shape == (1, 4) and np.array_equal(G1[0], [0.0, 1.0, 0.0, 0.0]) and c1[0] == 2.0
+
+
+def test_project_oa_encloses_the_taylor_model():
+    rng = np.random.default_rng(11)
+    exps, coeffs, rem, dt = _random_taylor_models(rng, 5, 3, 4, 3)
+    for i in range(5):
+        c, G = dz.project_oa_taylor_model(exps, coeffs[i], rem[i], dt[i], [0, 2])
+        lo, hi = dz.low_high(c, G)
+        xi = rng.uniform(-1, 1, size=(200, 3)); xi[:8] = np.array(list(__import__("itertools").product([-1, 1], repeat=3)))
+        for x in xi:
+            val = dz.eval_taylor_model_point(exps, coeffs[i], dt[i], x)[[0, 2]]
+            assert np.all(val + rem[i][[0, 2], 0] >= lo - 1e-12) and np.all(val + rem[i][[0, 2], 1] <= hi + 1e-12)
