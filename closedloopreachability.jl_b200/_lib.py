@@ -18,7 +18,7 @@ SYMBOLS = [
     "clr_create", "clr_destroy", "clr_last_error", "clr_stream", "clr_synchronize", "clr_launch_count",
     "clr_device_alloc", "clr_device_free", "clr_memcpy_h2d", "clr_memcpy_d2h", "clr_set_tile_cells",
     "clr_set_profiling", "clr_last_pass_info", "clr_set_reorder",
-    "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_zonotopes",
+    "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_zonotopes", "clr_deepz_zonotopes_padded",
     "clr_deepz_fetch_zonotopes", "clr_deepz_fetch_reduced", "clr_project_oa", "clr_forward_points", "clr_rollout",
     "clr_plant_compile", "clr_plant_free", "clr_rollout_plant",
 ]
@@ -85,6 +85,8 @@ def lib():
     L.clr_deepz_boxgrid.restype = i32
     L.clr_deepz_zonotopes.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
     L.clr_deepz_zonotopes.restype = i32
+    L.clr_deepz_zonotopes_padded.argtypes = [vp, vp, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32]
+    L.clr_deepz_zonotopes_padded.restype = i32
     L.clr_deepz_fetch_zonotopes.argtypes = [vp, vp, vp, vp]
     L.clr_deepz_fetch_zonotopes.restype = i32
     L.clr_deepz_fetch_reduced.argtypes = [vp, i32, vp, vp, i32]

@@ -1028,6 +1028,35 @@ int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net_c, int32_t n, int64
     return run_deepz(ctx, net, c, in, p0max, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags);
 }
 
+int32_t clr_deepz_zonotopes_padded(clr_ctx* ctx, const clr_net* net_c, int32_t n, int64_t N, const double* C, const double* G,
+                                   const int32_t* ncols, int32_t cap, const clr_prepost* pp, double* out_lo, double* out_hi,
+                                   double* hull_lo, double* hull_hi, clr_stats* stats, int32_t keep_cap, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    clr_net* net = const_cast<clr_net*>(net_c);
+    if (!net || N < 0 || n < 1 || cap < 0) return fail(ctx, CLR_ERR_ARG, "clr_deepz_zonotopes_padded: bad argument");
+    if (N > 0 && (!C || !ncols || (cap > 0 && !G))) return fail(ctx, CLR_ERR_ARG, "clr_deepz_zonotopes_padded: NULL argument");
+    if (cap > CLR_NCOL_MAX - 8) return fail(ctx, CLR_ERR_ARG, "cap = %d generators per cell; at most %d supported", cap, CLR_NCOL_MAX - 8);
+    CU(cudaSetDevice(ctx->device));
+    Compiled* c = nullptr;
+    int rc = compile_net(ctx, net, pp, n, &c);
+    if (rc) return rc;
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    DeepzInput in{};
+    in.kind = 1; in.n = n; in.N = N; in.pad_cap = cap;
+    ctx->bounce_open = !dev_io; ctx->bounce_used = ctx->bounce_flushed = 0;
+    if (N > 0) {
+        const void *dC, *dG, *dN;
+        if (!dev_io)
+            for (int64_t i = 0; i < N; i++)
+                if (ncols[i] < 0 || ncols[i] > cap) return fail(ctx, CLR_ERR_ARG, "ncols[%lld] = %d outside 0..cap = %d", (long long)i, ncols[i], cap);
+        if ((rc = stage_in(ctx, 0, C, sizeof(double) * (size_t)n * N, dev_io, &dC))) return rc;
+        if ((rc = stage_in(ctx, 1, ncols, sizeof(int32_t) * (size_t)N, dev_io, &dN))) return rc;
+        if ((rc = stage_in(ctx, 2, G, sizeof(double) * (size_t)n * cap * N, dev_io, &dG))) return rc;
+        in.C = (const double*)dC; in.ncols = (const int*)dN; in.G = (const double*)dG; in.col_off = nullptr;
+    }
+    return run_deepz(ctx, net, c, in, cap, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags);
+}
+
 int32_t clr_deepz_fetch_zonotopes(clr_ctx* ctx, int32_t* out_ncols, double* out_c, double* out_G) {
     if (!ctx) return CLR_ERR_ARG;
     if (ctx->keep_cells <= 0) return fail(ctx, CLR_ERR_STATE, "no kept zonotopes: run a DeepZ call with keep_cap > 0 first");

@@ -410,7 +410,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         for (int d = 0; d < n; d++) p += tmpR[ci * n + d] != 0.0;
                     } else {
                         const long long cell = S.cellId[ci];
-                        p = (int)(in.col_off[cell + 1] - in.col_off[cell]);
+                        p = in.col_off ? (int)(in.col_off[cell + 1] - in.col_off[cell]) : in.ncols[cell];
                     }
                     w[h] = 1 + p;
                 }
@@ -494,7 +494,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     const int ci = it / rows4, d = it - ci * rows4;
                     const int cb = colOff[ci], p = S.wUsed[0][ci] - 1;
                     const long long cell = S.cellId[ci];
-                    const long long go = in.col_off[cell];
+                    const long long go = in.col_off ? in.col_off[cell] : cell * (long long)in.pad_cap;
                     cur[cb * P + d] = d < n ? in.C[cell * n + d] : 0.0;
                     for (int j = 0; j < p; j++) cur[(cb + 1 + j) * P + d] = d < n ? in.G[(go + j) * n + d] : 0.0;
                 }

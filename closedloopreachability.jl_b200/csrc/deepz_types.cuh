@@ -16,6 +16,8 @@ struct DeepzInput {
     const double* C;          // device, n x N
     const long long* col_off; // device, N + 1
     const double* G;          // device, n x col_off[N]
+    const int* ncols;         // padded layout (col_off == nullptr): generators of cell i are ncols[i] columns at G + i * pad_cap * n
+    int pad_cap;
 };
 
 struct DeepzOutput {

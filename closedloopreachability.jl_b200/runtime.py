@@ -276,6 +276,41 @@ class Context:
             out.update(self.fetch_zonotopes(N, m, keep_cap))
         return out
 
+    def deepz_zonotopes_padded(self, dnet: DeviceNetwork, Cc, G, ncols, pre=None, post=None, hull=False, stats=True, keep_cap=0):
+        """Zonotope cells in the padded layout of ``project_oa`` / ``fetch_zonotopes``: Cc (N, n), G (N, cap, n) with the first
+        ncols[i] rows of G[i] the generators of cell i."""
+        Cc = np.ascontiguousarray(Cc, dtype=np.float64)
+        G = np.ascontiguousarray(G, dtype=np.float64)
+        ncols = np.ascontiguousarray(ncols, dtype=np.int32)
+        if Cc.ndim != 2 or G.ndim != 3 or G.shape[0] != Cc.shape[0] or G.shape[2] != Cc.shape[1] or ncols.shape != (Cc.shape[0],):
+            raise ClrArgumentError(ERR_DIM, "padded zonotopes: Cc (N, n), G (N, cap, n), ncols (N,)")
+        N, n = Cc.shape
+        pp = PrePostArg(pre, post)
+        m = pp.out_dim(dnet.dims[-1])
+        lo = np.empty((N, m)); hi = np.empty((N, m))
+        hl = np.empty(m) if hull else None
+        hh = np.empty(m) if hull else None
+        st = _lib.Stats() if stats else None
+        self._check(self.L.clr_deepz_zonotopes_padded(self.h, dnet.h, n, N, _ptr(Cc), _ptr(G), _ptr(ncols), G.shape[1], C.byref(pp.s),
+                                                      _ptr(lo), _ptr(hi), _ptr(hl), _ptr(hh), C.byref(st) if stats else None,
+                                                      int(keep_cap), 0 if stats else FLAG_NO_STATS))
+        out = {"lo": lo, "hi": hi}
+        if hull:
+            out.update(hull_lo=hl, hull_hi=hh)
+        if stats:
+            out["stats"] = stats_dict(st, len(dnet.net.layers))
+        if keep_cap:
+            out.update(self.fetch_zonotopes(N, m, keep_cap))
+        return out
+
+    def deepz_zonotopes_padded_dev(self, dnet, n, N, d_C, d_G, d_ncols, cap, pp: PrePostArg, d_lo, d_hi, d_hull_lo=None,
+                                   d_hull_hi=None, stats=None, keep_cap=0):
+        """Device-resident variant: chains the outputs of ``project_oa_dev`` into the controller propagation."""
+        flags = FLAG_DEVICE_IO | (0 if stats is not None else FLAG_NO_STATS)
+        self._check(self.L.clr_deepz_zonotopes_padded(self.h, dnet.h, int(n), int(N), _ptr(d_C), _ptr(d_G), _ptr(d_ncols), int(cap),
+                                                      C.byref(pp.s), _ptr(d_lo), _ptr(d_hi), _ptr(d_hull_lo), _ptr(d_hull_hi),
+                                                      C.byref(stats) if stats is not None else None, int(keep_cap), flags))
+
     def fetch_zonotopes(self, N, m, keep_cap):
         nc = np.zeros(N, dtype=np.int32)
         c = np.zeros((N, m))

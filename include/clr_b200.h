@@ -158,6 +158,13 @@ int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net, int32_t n, int64_t
                             double* out_lo, double* out_hi, double* hull_lo, double* hull_hi,
                             clr_stats* stats, int32_t keep_cap, int32_t flags);
 
+/* Same for zonotopes in the padded layout that clr_project_oa and clr_deepz_fetch_zonotopes produce: generators of cell i are
+   the first ncols[i] columns of the n x cap block at G + i*cap*n.  With CLR_FLAG_DEVICE_IO the output arrays of
+   clr_project_oa feed this call directly (the cells of control period k + 1 never visit the host, src/solve.jl:181-195). */
+int32_t clr_deepz_zonotopes_padded(clr_ctx* ctx, const clr_net* net, int32_t n, int64_t N, const double* C, const double* G,
+                                   const int32_t* ncols, int32_t cap, const clr_prepost* pp, double* out_lo, double* out_hi,
+                                   double* hull_lo, double* hull_hi, clr_stats* stats, int32_t keep_cap, int32_t flags);
+
 /*
  * Output zonotopes of the last keep_cap > 0 run: out_ncols (N), out_c (m_out x N),
  * out_G (m_out x keep_cap x N: generator j of cell i at out_G + (i*keep_cap + j)*m_out).

@@ -129,7 +129,8 @@ live chains of a control period (src/solve.jl:181-184): one call instead of one 
 `TaylorModel1{TaylorN{Float64},Float64}`; its time coefficient k contributes `vcat((c.coeffs for c in p[k].coeffs)...)`
 (all homogeneous polynomials, degree 0 first -- TaylorSeries' coefficient order), the exponent table is
 `reduce(hcat, vcat(TaylorSeries.coeff_table...))`, and dt = t - tstart(R).  Returns the centres (n_keep x N), the
-generators (n_keep x 2n x N) and the generator counts: the arguments `clr_deepz_zonotopes` takes for the next period.
+generators (n_keep x 2n x N) and the generator counts: the arguments `clr_deepz_zonotopes_padded` takes for the next period
+(with CLR_FLAG_DEVICE_IO the two calls chain on the device).
 """
 function project_oa_batch(ctx::Context, exps::Matrix{Int32}, coeffs::Array{Float64,4}, rem::Array{Float64,3}, dt::Vector{Float64},
                           vars::Vector{Int32}; remove_zero_generators::Bool=true)

@@ -521,5 +521,24 @@ def test_project_oa_batched(ctx):
     out = ctx.deepz_zonotopes(dn, big["c"][sub], col_off, Gp, post=("shift", -10.0))
     ref = _oracle().deepz_zonotopes(_oracle().Net(net.as_tuples()), big["c"][sub], col_off, Gp, post=("shift", -10.0))
     _cmp_boxes(out, ref)
+    # the same cells in the padded layout (no host-side compaction): bit-identical boxes
+    outp = ctx.deepz_zonotopes_padded(dn, big["c"][sub], big["G"][sub], nc, post=("shift", -10.0))
+    assert np.array_equal(outp["lo"], out["lo"]) and np.array_equal(outp["hi"], out["hi"])
+    assert outp["stats"]["sum_p_in"] == out["stats"]["sum_p_in"]
+    # ... and fully on the device: clr_project_oa -> clr_deepz_zonotopes_padded with CLR_FLAG_DEVICE_IO
+    import torch
+    from clr_b200 import runtime
+    dev = torch.device("cuda", 0)
+    M5 = 500
+    d_coef = torch.from_numpy(coeffs[:M5]).to(dev); d_rem = torch.from_numpy(rem[:M5]).to(dev); d_dt = torch.from_numpy(dt[:M5]).to(dev)
+    d_c = torch.empty((M5, 4), dtype=torch.float64, device=dev); d_G = torch.empty((M5, 2 * n, 4), dtype=torch.float64, device=dev)
+    d_nc = torch.empty((M5,), dtype=torch.int32, device=dev)
+    d_lo = torch.empty((M5, 1), dtype=torch.float64, device=dev); d_hi = torch.empty_like(d_lo)
+    ctx.project_oa_dev(n, 4, exps, M5, d_coef, d_rem, d_dt, vk, True, d_c, d_G, d_nc)
+    ctx.deepz_zonotopes_padded_dev(dn, 4, M5, d_c, d_G, d_nc, 2 * n, runtime.PrePostArg(None, ("shift", -10.0)), d_lo, d_hi)
+    ctx.synchronize()
+    assert np.array_equal(d_lo.cpu().numpy(), out["lo"]) and np.array_equal(d_hi.cpu().numpy(), out["hi"])
     with pytest.raises(Exception):
         ctx.project_oa(exps, coeffs, rem, dt, [7])           # variable outside 0..n-1
+    with pytest.raises(Exception):
+        ctx.deepz_zonotopes_padded(dn, big["c"][:2], big["G"][:2], np.array([99, 0], dtype=np.int32))   # ncols > cap
