@@ -647,6 +647,13 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     sp.inplace = c->inplace;
     for (int l = 0; l < D.L; l++)      // every sigmoid / tanh neuron appends a generator (unless its bounds coincide)
         if (D.layer[l].act == CLR_ACT_SIGMOID || D.layer[l].act == CLR_ACT_TANH) sp.grow_cols += D.layer[l].m;
+    {
+        // the last layer applied column by column in the output stage (deepz_kernel): a final Id layer with at most 4 inputs and
+        // rows (the folded post-processing) that the reference does not follow by remove_zero_columns; kept zonotopes need the
+        // real columns
+        const DevLayer& lt = D.layer[D.L - 1];
+        sp.fuse_tail = D.L >= 2 && lt.act == CLR_ACT_ID && lt.m <= 4 && lt.n <= 4 && !lt.remove_zero && keep_cap == 0;
+    }
     sp.retry_list = ctx->d_retry;
     sp.big_list = ctx->d_big;
     sp.workspace = nullptr;

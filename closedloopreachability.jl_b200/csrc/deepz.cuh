@@ -303,6 +303,10 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
     const bool useHull = out.hull_lo != nullptr && mOut <= CLR_HULL_MAX;
     const bool needDead = STATS;                  // kept zonotopes are only written by the STATS instantiations
     const int stageW = max(clr_pad4(net->max_rows), 2 * n);   // doubles of staging per cell
+    // A final Id layer with at most 4 rows (the scalar control of most models, or the folded post-processing) does not get a
+    // product / relaxation / layout cycle of its own: it is a dot product per column, applied in the output stage.
+    const bool fuse = sp.fuse_tail != 0;
+    const int Lrun = fuse ? L - 1 : L;
 
     // ---- one-time setup: layer descriptors to smem, accumulators, the first tile ------------------
     for (int i = tid; i < L * (int)(sizeof(DevLayer) / sizeof(int)); i += NT) ((int*)S.layers)[i] = ((const int*)net->layer)[i];
@@ -513,7 +517,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         // appended by the previous relaxation pending in mask[flip] / stage, next layout in colOff[flip ^ 1], colPos maps
         // current -> next columns
         bool tileDead = false;
-        for (int l = 0; l < L; l++) {
+        for (int l = 0; l < Lrun; l++) {
             const DevLayer& Ly = S.layers[l];
             const int* offNxt = S.colOff[flip ^ 1];
             const unsigned short* wCur = S.wUsed[flip];
@@ -598,7 +602,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             for (int i = tid; i < nCells * DZ_MASK_STRIDE; i += NT) (&fresh[0][0])[i] = 0;
             if (tid == 0) S.kActNew = 0;
             // weights of the next layer (or of the first layer for the next tile) while the relaxation runs
-            dz_load_a<KSREG>(S.layers[l + 1 < L ? l + 1 : 0], warp, lane, nWarps, a);
+            dz_load_a<KSREG>(S.layers[l + 1 < Lrun ? l + 1 : 0], warp, lane, nWarps, a);
             if (needDead) {
                 // dead marks follow their columns to the new positions
                 unsigned* dOld = S.deadMask[flipD];
@@ -722,10 +726,20 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
             DZ_T(3);
             // ---- next layout (every warp computes it; warp 0 publishes it) and the position table -----------------------
-            {
+            if (l + 1 == Lrun) {
+                // no product follows the last layer: only the widths the output stage reads
+                if (tid < nCells) {
+                    int u = 0;
+                    for (int ww = 0; ww < mw; ww++) u += __popc(fresh[tid][ww]);
+                    S.wUsed[flip ^ 1][tid] = (unsigned short)(collapse ? 2 : wCur[tid] + S.uPend[flip][tid]);
+                    S.uPend[flip ^ 1][tid] = (unsigned short)u;
+                    if (STATS && Ly.net_layer >= 0) S.cellUnst[tid][Ly.net_layer] = (unsigned short)u;
+                }
+                if (tid == 0) S.kAct = S.kActNew;
+            } else {
                 int off0, off1, keep, total;
                 int w[2] = {0, 0}, wu[2] = {0, 0}, uu[2] = {0, 0};
-                const int minW = (l + 1 < L && S.layers[l + 1].collapse) ? 2 : 1;   // a one-row map writes [c, r]
+                const int minW = (l + 1 < Lrun && S.layers[l + 1].collapse) ? 2 : 1;   // a one-row map writes [c, r]
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int ci = lane + 32 * h;
@@ -825,6 +839,42 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         {
             const int* colOff = S.colOff[flip];
             const unsigned* dead = S.deadMask[flipD];
+            const DevLayer& Lt = S.layers[L - 1];
+            const bool tailCollapse = fuse && Lt.collapse;
+            if (fuse) {
+                const int nt = Lt.n, mt = Lt.m;
+                if (STATS && Lt.net_layer >= 0 && tid < nCells) {
+                    // generators entering the fused layer, as the reference counts them
+                    const int cb = colOff[tid], w = S.wUsed[flip][tid];
+                    int nz = 0;
+                    for (int j = 1; j < w; j++) nz += !((dead[(cb + j) >> 5] >> ((cb + j) & 31)) & 1u);
+                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) nz += __popc(S.mask[flip][tid][ww]);
+                    S.cellPin[tid][Lt.net_layer] = (unsigned short)nz;
+                    S.cellUnst[tid][Lt.net_layer] = 0;
+                }
+                // W x for every used column, in place: rows 0 .. mt-1 of the column become its image.  The fused layer has
+                // at most 4 inputs (post-processing, or a layer behind a one-row layer): a thread per column, k ascending.
+                for (int col = tid; col < nCols; col += NT) {
+                    int lo_ = 0, hi_ = nCells;                 // cell of this column: the last ci with colOff[ci] <= col
+                    while (hi_ - lo_ > 1) { const int mid = (lo_ + hi_) >> 1; if (colOff[mid] <= col) lo_ = mid; else hi_ = mid; }
+                    const int j = col - colOff[lo_];
+                    if (j >= S.wUsed[flip][lo_]) continue;
+                    double* x = cur + col * P;
+                    double xv[4], yv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) xv[k] = k < nt ? x[k] : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        double sacc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if (k < nt && r < mt) sacc += __ldg(Lt.Wcm + (size_t)k * mt + r) * xv[k];
+                        yv[r] = (j == 0 && r < mt) ? sacc + __ldg(Lt.bias + r) : sacc;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; r++) if (r < mt) x[r] = yv[r];
+                }
+                __syncthreads();
+            }
             // ranks of the surviving output generators (remove_zero_columns); the position table is free now
             unsigned short* colRank = S.colPos;
             int* rank0 = S.colOff[flip ^ 1];              // rank of a cell's first pending generator
@@ -840,7 +890,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     int u = 0;
                     for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[flip][tid][ww]);
                     rank0[tid] = k;
-                    if (STATS) atomicMax(&S.sMaxP, k + u);
+                    if (STATS) atomicMax(&S.sMaxP, tailCollapse ? 1 : k + u);      // a one-row map returns a single generator
                     if (STATS && out.keep_cap > 0) {
                         out.keepN[S.cellId[tid]] = k + u;
                         if (k + u > out.keep_cap) atomicCAS(&st->error, 0, (int)CLR_ERR_CAPACITY);
@@ -853,10 +903,39 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 const int cb = colOff[ci], w = S.wUsed[flip][ci];
                 const double* y = cur + cb * P + r;
                 const unsigned mwv = S.mask[flip][ci][r >> 5];
-                const bool pend = (mwv >> (r & 31)) & 1u;     // this row's own appended generator mu * e_r
+                const bool pend = !fuse && ((mwv >> (r & 31)) & 1u);     // this row's own appended generator mu * e_r
                 const double mu = pend ? stage[ci * stageW + r] : 0.0;
                 double c = y[0], lo, hi;
-                if (mOut == 1) {
+                if (fuse) {
+                    // the columns hold W x already; the generators appended by the last relaxation are mu_i e_i, their
+                    // images mu_i W[r, i] come after them, in ascending i (the order of the materialised columns)
+                    const int mwN = (Lt.n + 31) >> 5;
+                    if (mOut == 1 && !tailCollapse) {
+                        lo = c; hi = c;
+                        for (int j = 1; j < w; j++) { double av = fabs(y[j * P]); lo -= av; hi += av; }
+                        for (int ww = 0; ww < mwN; ww++) {
+                            unsigned bits = S.mask[flip][ci][ww];
+                            while (bits) {
+                                const int i = ww * 32 + __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                const double av = fabs(stage[ci * stageW + i] * __ldg(Lt.Wcm + (size_t)i * mOut + r));
+                                lo -= av; hi += av;
+                            }
+                        }
+                    } else {
+                        double rad = 0.0;
+                        for (int j = 1; j < w; j++) rad += fabs(y[j * P]);
+                        for (int ww = 0; ww < mwN; ww++) {
+                            unsigned bits = S.mask[flip][ci][ww];
+                            while (bits) {
+                                const int i = ww * 32 + __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                rad += fabs(stage[ci * stageW + i] * __ldg(Lt.Wcm + (size_t)i * mOut + r));
+                            }
+                        }
+                        lo = c - rad; hi = c + rad;
+                    }
+                } else if (mOut == 1) {
                     lo = c; hi = c;
                     for (int j = 1; j < w; j++) { double av = fabs(y[j * P]); lo -= av; hi += av; }
                     if (pend) { lo -= fabs(mu); hi += fabs(mu); }

@@ -38,6 +38,7 @@ struct DeepzSched {
     int cap;                  // doubles of column store (+ staging) per CTA
     int inplace;              // 1: layer products run in place (every warp owns at most one row block)
     int grow_cols;            // generators every cell is known to gain (sigmoid / tanh layers append one per neuron)
+    int fuse_tail;            // 1: the last layer (Id, at most 4 inputs and rows) is applied column by column in the output stage
     long long* retry_list;
     long long* big_list;
     double* workspace;        // pass 2: gridDim.x * cap doubles
