@@ -51,12 +51,27 @@ __global__ void __launch_bounds__(RD_WARPS * 32) reduce_order_kernel(ReduceArgs 
                 wgt[j] = s - mx;
             }
             __syncwarp();
-            // stable descending order by counting: position of j = #{k : w_k > w_j, or w_k == w_j and k < j}
-            for (int j = lane; j < p; j += 32) {
-                const double wj = wgt[j];
-                int pos = 0;
-                for (int k = 0; k < p; k++) { const double wk = wgt[k]; pos += (wk > wj) || (wk == wj && k < j); }
-                sorted[pos] = j;
+            // stable descending order by counting: position of j = #{k : w_k > w_j, or w_k == w_j and k < j}.
+            // A lane ranks 8 of its generators at once (registers), so every weight is read once per 256 generators.
+            for (int j0 = 0; j0 < p; j0 += 256) {
+                double wj[8];
+                int pos[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int j = j0 + q * 32 + lane;
+                    wj[q] = j < p ? wgt[j] : -1.0;             // weights are >= 0: a padded slot is never counted below
+                    pos[q] = 0;
+                }
+                for (int k = 0; k < p; k++) {
+                    const double wk = wgt[k];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) pos[q] += (wk > wj[q]) || (wk == wj[q] && k < j0 + q * 32 + lane);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int j = j0 + q * 32 + lane;
+                    if (j < p) sorted[pos[q]] = j;
+                }
             }
             __syncwarp();
         }
