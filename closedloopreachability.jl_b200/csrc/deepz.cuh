@@ -183,11 +183,12 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
             unsigned pos[NB][2];
 #pragma unroll
             for (int j = 0; j < NB; j++) {
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int col = cg * NB * 8 + j * 8 + qc * 2 + e;
-                    pos[j][e] = (mine && col < nCols && ((blkMask >> j) & 1u)) ? colPos[col] : 0xFFFFu;
-                }
+                // this thread's two columns are neighbours: one 32-bit load for both positions
+                const int col0 = cg * NB * 8 + j * 8 + qc * 2;
+                unsigned pp = 0xFFFFFFFFu;
+                if (mine && col0 < nCols && ((blkMask >> j) & 1u)) pp = *reinterpret_cast<const unsigned*>(colPos + col0);
+                pos[j][0] = pp & 0xFFFFu;
+                pos[j][1] = col0 + 1 < nCols ? pp >> 16 : 0xFFFFu;
             }
             if (inplace) {
                 // everybody has read group cg (and all groups behind it): only then may its results, which land
