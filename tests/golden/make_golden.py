@@ -64,6 +64,25 @@ def main():
     c, G = dz.deepz_forward(quad, c, G)
     np.savez_compressed(os.path.join(HERE, "quadrotor_oracle.npz"), lo=l, hi=h, cell0_c=c, cell0_G=G)
 
+    # order-2 / order-3 reduction of that output zonotope (src/setops.jl:84-86) and _project_oa
+    # (src/setops.jl:9-12) of a fixed batch of Taylor models (seeded; TMJets-like orders 4 / 2 in 3 variables)
+    out = {}
+    for order in (1, 2, 3):
+        rc, rG = dz.reduce_order_gir05(c, G, order)
+        out[f"red{order}_c"], out[f"red{order}_G"] = rc, rG
+    rng = np.random.default_rng(77)
+    n, oT, oQ, N = 3, 4, 2, 6
+    exps = dz.monomial_table(n, oQ)
+    deg = exps.sum(axis=1)
+    coeffs = rng.normal(size=(N, n, oT + 1, exps.shape[0])) * (0.1 ** deg)[None, None, None, :] / (1.0 + np.arange(oT + 1))[None, None, :, None]
+    rem = np.sort(rng.normal(size=(N, n, 2)) * 1e-6, axis=2)
+    dt = rng.uniform(0.05, 0.2, size=N)
+    out.update(tm_exps=exps, tm_coeffs=coeffs, tm_rem=rem, tm_dt=dt)
+    for i in range(N):
+        pc, pG = dz.project_oa_taylor_model(exps, coeffs[i], rem[i], dt[i], [0, 2])
+        out[f"proj{i}_c"], out[f"proj{i}_G"] = pc, pG
+    np.savez_compressed(os.path.join(HERE, "setops_oracle.npz"), **out)
+
 
 if __name__ == "__main__":
     main()

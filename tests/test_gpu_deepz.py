@@ -542,3 +542,15 @@ def test_project_oa_batched(ctx):
         ctx.project_oa(exps, coeffs, rem, dt, [7])           # variable outside 0..n-1
     with pytest.raises(Exception):
         ctx.deepz_zonotopes_padded(dn, big["c"][:2], big["G"][:2], np.array([99, 0], dtype=np.int32))   # ncols > cap
+
+
+def test_setops_golden_fixture_on_the_device(ctx):
+    """clr_project_oa against the committed fixture (tests/golden/setops_oracle.npz)."""
+    z = np.load(os.path.join(GOLDEN, "setops_oracle.npz"))
+    got = ctx.project_oa(z["tm_exps"], z["tm_coeffs"], z["tm_rem"], z["tm_dt"], [0, 2])
+    for i in range(z["tm_dt"].shape[0]):
+        G = z[f"proj{i}_G"]
+        assert got["ncols"][i] == G.shape[1]
+        scale = max(np.abs(G).max(), np.abs(z[f"proj{i}_c"]).max())
+        np.testing.assert_allclose(got["c"][i], z[f"proj{i}_c"], rtol=0, atol=1e-12 * scale)
+        np.testing.assert_allclose(got["G"][i, :G.shape[1]].T, G, rtol=0, atol=1e-12 * scale)

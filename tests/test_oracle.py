@@ -256,3 +256,18 @@ def test_project_oa_encloses_the_taylor_model():
         for x in xi:
             val = dz.eval_taylor_model_point(exps, coeffs[i], dt[i], x)[[0, 2]]
             assert np.all(val + rem[i][[0, 2], 0] >= lo - 1e-12) and np.all(val + rem[i][[0, 2], 1] <= hi + 1e-12)
+
+
+def test_setops_golden_fixture():
+    """Regression pins of the 8f restatements (tests/golden/setops_oracle.npz, written by make_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, "setops_oracle.npz"))
+    q = np.load(os.path.join(GOLDEN, "quadrotor_oracle.npz"))
+    ncols = np.array([q["cell0_G"].shape[1]], dtype=np.int32)
+    for order in (1, 2, 3):
+        rc, rG = dz.reduce_order_gir05(q["cell0_c"], q["cell0_G"], order)
+        assert np.array_equal(rG, z[f"red{order}_G"]) and np.array_equal(rc, z[f"red{order}_c"])
+        oc, oG = cbind.reduce_order(ncols, q["cell0_c"][None, :], q["cell0_G"].T[None, :, :], order)
+        assert np.array_equal(oG[0].T, z[f"red{order}_G"])
+    for i in range(z["tm_dt"].shape[0]):
+        pc, pG = dz.project_oa_taylor_model(z["tm_exps"], z["tm_coeffs"][i], z["tm_rem"][i], z["tm_dt"][i], [0, 2])
+        assert np.array_equal(pc, z[f"proj{i}_c"]) and np.array_equal(pG, z[f"proj{i}_G"])
