@@ -554,3 +554,28 @@ def test_setops_golden_fixture_on_the_device(ctx):
         scale = max(np.abs(G).max(), np.abs(z[f"proj{i}_c"]).max())
         np.testing.assert_allclose(got["c"][i], z[f"proj{i}_c"], rtol=0, atol=1e-12 * scale)
         np.testing.assert_allclose(got["G"][i, :G.shape[1]].T, G, rtol=0, atol=1e-12 * scale)
+
+
+def test_cells_too_large_for_shared_memory_take_the_global_store_pass(ctx):
+    """Zonotopes with 400 generators entering TORA's 100-neuron layers: after the first relaxations a cell is several
+    hundred columns of 100 rows, more than an SM's shared memory holds: the retry and the global-store passes run (with the
+    folded -10 shift applied in the output stage) and still agree with the oracle; a run that keeps the zonotopes (the
+    shift as a real layer) returns the same boxes."""
+    from clr_b200 import workloads
+    net = load_net("TORA_ReLU")
+    dn = ctx.upload(net)
+    rng = np.random.default_rng(5)
+    C, off, G = workloads.random_zonotopes(rng, 40, 4, 380, 400, -0.6, 0.6, 0.004)
+    ctx.set_profiling(True)
+    try:
+        got = ctx.deepz_zonotopes(dn, C, off, G, post=("shift", -10.0), hull=True)
+        info = ctx.last_pass_info()
+    finally:
+        ctx.set_profiling(False)
+    assert info["big"] > 0, info
+    ref = _oracle().deepz_zonotopes(_oracle().Net(net.as_tuples()), C, off, G, post=("shift", -10.0))
+    _cmp_boxes(got, ref)
+    assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"] and got["stats"]["sum_unstable"] == ref["stats"]["sum_unstable"]
+    assert got["hull_lo"][0] == got["lo"].min() and got["hull_hi"][0] == got["hi"].max()
+    kept = ctx.deepz_zonotopes(dn, C, off, G, post=("shift", -10.0), keep_cap=1024)
+    assert np.array_equal(kept["lo"], got["lo"]) and np.array_equal(kept["hi"], got["hi"])
