@@ -47,6 +47,25 @@ def parse():
     return ap.parse_args()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line (the driver's contract).  Libraries write there too (NCCL prints its version
+    banner on stdout when NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the whole run and
+    the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -176,7 +195,7 @@ def run_reference(args):
                              "sample": f"{per_step} cells per step x {args.steps} steps; the reference is Julia "
                                        "(absent from this image), so its C restatement in oracle/ is timed"},
             "e2e": {"value": v, "unit": "propagations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -186,9 +205,6 @@ def run_ours(args):
     rank, local, world = dist_env()
     import torch.distributed as dist
     if world > 1:
-        # NCCL logs (e.g. its version banner when NCCL_DEBUG is set on the box) go to stdout by default: keep stdout for
-        # the ONE JSON line of the contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -347,7 +363,7 @@ def run_ours(args):
                              "control periods, 4->500->2 ReLU controller; Tsit5 = the reference's solver, RK4 = 4 fixed steps / period",
                              **res}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -355,6 +371,7 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
+    claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
