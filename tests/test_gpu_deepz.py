@@ -186,6 +186,11 @@ def test_degenerate_cells_equal_pointwise_forward(ctx):
         u = ctx.forward_points(dn, X)
         np.testing.assert_allclose(r["lo"], u, rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose(r["hi"], u, rtol=1e-12, atol=1e-14)
+        # the padded layout with no generator capacity at all, and an empty batch
+        rp = ctx.deepz_zonotopes_padded(dn, X, np.zeros((50, 0, net.dim_in)), np.zeros(50, dtype=np.int32))
+        assert np.array_equal(rp["lo"], r["lo"]) and np.array_equal(rp["hi"], r["hi"])
+        re = ctx.deepz_zonotopes_padded(dn, X[:0], np.zeros((0, 3, net.dim_in)), np.zeros(0, dtype=np.int32))
+        assert re["lo"].shape == (0, r["lo"].shape[1])
 
 
 def test_shards_concatenate_to_the_full_result(ctx):
