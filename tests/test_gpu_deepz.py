@@ -391,7 +391,7 @@ def test_random_networks_fuzz(ctx):
     from clr_b200 import workloads
     rng = np.random.default_rng(2024)
     acts = ["Id", "ReLU", "Sigmoid", "Tanh"]
-    for trial in range(36):
+    for trial in range(int(os.environ.get("CLR_FUZZ_TRIALS", "36"))):
         depth = int(rng.integers(1, 6))
         n_in = int(rng.integers(1, 9))
         dims = [n_in] + [int(rng.choice([1, 2, 3, 7, 8, 9, 16, 20, 33, 64, 100, 130])) for _ in range(depth)]
@@ -432,6 +432,20 @@ def test_random_networks_fuzz(ctx):
         gs = max(np.abs(ref["G"]).max(), np.abs(ref["c"]).max(), 1e-300)
         np.testing.assert_allclose(np.abs(got["G"]), np.abs(ref["G"]), rtol=0, atol=1e-12 * gs, err_msg=str(info))
         np.testing.assert_allclose(got["c"], ref["c"], rtol=0, atol=1e-12 * gs, err_msg=str(info))
+        # the same cells as a box-only call (small-call path, lean / no-statistics instantiations, post-processing applied
+        # in the output stage): same boxes within the tolerance, hull = min / max of the cells
+        st = trial % 4 < 2
+        if trial % 2 == 0:
+            box = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, pre=pre, post=post, hull=True, stats=st)
+        else:
+            box = ctx.deepz_zonotopes(dn, C, off, G, pre=pre, post=post, hull=True, stats=st)
+        np.testing.assert_allclose(box["lo"], ref["lo"], rtol=0, atol=BOX_ATOL * scale, err_msg=str(info))
+        np.testing.assert_allclose(box["hi"], ref["hi"], rtol=0, atol=BOX_ATOL * scale, err_msg=str(info))
+        np.testing.assert_array_equal(box["hull_lo"], box["lo"].min(0))
+        np.testing.assert_array_equal(box["hull_hi"], box["hi"].max(0))
+        if st:
+            assert box["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"], info
+            assert box["stats"]["max_p_out"] == ref["stats"]["max_p_out"], info
 
 
 def test_order2_reduction_of_kept_zonotopes(ctx):
