@@ -638,12 +638,19 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                             }
                         }
                     } else if (FULL && (act == CLR_ACT_SIGMOID || act == CLR_ACT_TANH)) {
-                        double ly = act == CLR_ACT_SIGMOID ? dz_sigm(lo) : tanh(lo);
-                        double uy = act == CLR_ACT_SIGMOID ? dz_sigm(hi) : tanh(hi);
+                        // the transcendental calls side by side, so that their (independent) instruction chains interleave;
+                        // the same formulas and values as dz_sigm / dz_sigm_p / dz_tanh_p
+                        double ly, uy, dl, du;
+                        if (act == CLR_ACT_SIGMOID) {
+                            const double eml = exp(-lo), emh = exp(-hi), el = exp(lo), eh = exp(hi);
+                            ly = 1.0 / (1.0 + eml); uy = 1.0 / (1.0 + emh);
+                            dl = el / ((1.0 + el) * (1.0 + el)); du = eh / ((1.0 + eh) * (1.0 + eh));
+                        } else {
+                            ly = tanh(lo); uy = tanh(hi);
+                            dl = 1.0 - ly * ly; du = 1.0 - uy * uy;
+                        }
                         if (dz_approx(lo, hi)) { cn = uy; la = 0.0; }
                         else {
-                            double dl = act == CLR_ACT_SIGMOID ? dz_sigm_p(lo) : dz_tanh_p(lo);
-                            double du = act == CLR_ACT_SIGMOID ? dz_sigm_p(hi) : dz_tanh_p(hi);
                             la = dl < du ? dl : du;
                             double mu1 = (uy + ly - la * (hi + lo)) / 2;
                             mm = (uy - ly - la * (hi - lo)) / 2;
