@@ -462,6 +462,24 @@ int worst_cols(const DevNet& D, int p0) {
 
 namespace {
 
+// Tile metadata of one launch (see DeepzSched): the appended-generator masks and the position table are sized for the network
+// and the shared memory at hand instead of for the largest supported tile (64 cells x 512 rows x 2048 columns) -- every KB
+// saved is column store.  ncol_need > 0 fixes the position table (global-store pass: cells wider than an SM's store).
+// Returns the bytes of dynamic shared memory in front of the column store.
+size_t dz_geom(const DevNet& D, bool stats, size_t smem_total, int ncol_need, DeepzSched& sp) {
+    const size_t fixed = dz_meta_bytes(stats);
+    sp.mask_words = std::max(1, (D.max_rows + 31) / 32);
+    sp.mask_stride = sp.mask_words | 1;
+    const long long avail_cols = smem_total > fixed ? (long long)((smem_total - fixed) / 8 / (size_t)D.max_pitch) : 0;
+    sp.tile_max = (int)std::max<long long>(4, std::min<long long>(CLR_TILE_CELLS_MAX, avail_cols / (sp.grow_cols + 2)));
+    sp.ncol_max = ncol_need > 0 ? std::min(CLR_NCOL_MAX, ncol_need)
+                                : (int)std::min<long long>(CLR_NCOL_MAX, ((avail_cols + 40 + 7) / 8) * 8);
+    size_t off = fixed + sizeof(unsigned) * 2 * (size_t)sp.tile_max * sp.mask_stride + sizeof(unsigned short) * ((size_t)sp.ncol_max + 32);
+    off = (off + 15) & ~(size_t)15;
+    sp.store_off = (int)off;
+    return off;
+}
+
 int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int grid, int threads, size_t smem,
                  const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
     cudaError_t e;
@@ -513,7 +531,7 @@ int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& 
     DeepzOutput out{};
     out.liveCount = ctx->d_live;
     DeepzSched sp{};
-    const size_t meta = dz_meta_bytes(false);
+    const size_t meta = dz_geom(D, false, (size_t)ctx->smem_optin, 0, sp);
     sp.cap = (int)(((size_t)ctx->smem_optin - meta) / 8);
     sp.tile_cells = 4;                    // fixed tiles: which cells a tile drops must not depend on the scheduling,
                                           // or the order (and the last bits of the results) would vary from call to call
@@ -638,15 +656,15 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     const int threads = DZ_THREADS;
     // kept zonotopes need the zero-generator bookkeeping, which only the STATS instantiations carry
     const bool kstats = want_stats || keep_cap > 0;
-    const size_t meta = dz_meta_bytes(kstats);
     const size_t smem_total = (size_t)ctx->smem_optin;
-    if (smem_total < meta + 8 * 1024) return fail(ctx, CLR_ERR_CUDA, "device has too little shared memory");
     DeepzSched sp{};
+    for (int l = 0; l < D.L; l++)      // every sigmoid / tanh neuron appends a generator (unless its bounds coincide)
+        if (D.layer[l].act == CLR_ACT_SIGMOID || D.layer[l].act == CLR_ACT_TANH) sp.grow_cols += D.layer[l].m;
+    const size_t meta = dz_geom(D, kstats, smem_total, 0, sp);
+    if (smem_total < meta + 8 * 1024) return fail(ctx, CLR_ERR_CUDA, "device has too little shared memory");
     sp.cap = (int)((smem_total - meta) / 8);
     sp.tile_cells = ctx->tile_cells;
     sp.inplace = c->inplace;
-    for (int l = 0; l < D.L; l++)      // every sigmoid / tanh neuron appends a generator (unless its bounds coincide)
-        if (D.layer[l].act == CLR_ACT_SIGMOID || D.layer[l].act == CLR_ACT_TANH) sp.grow_cols += D.layer[l].m;
     {
         // the last layer applied column by column in the output stage (deepz_kernel): a final Id layer with at most 4 inputs and
         // rows (the folded post-processing) that the reference does not follow by remove_zero_columns; kept zonotopes need the
@@ -698,8 +716,10 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         size_t need = sizeof(double) * (size_t)gridg * sg.cap;
         if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, need))) return rc;
         sg.workspace = ctx->d_ws;
+        const size_t metag = dz_geom(D, kstats, smem_total, wc + 8 + 40, sg);     // one wide cell per tile
+        if (metag > smem_total) return fail(ctx, CLR_ERR_CAPACITY, "a cell with %d columns exceeds the tile metadata", wc);
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        if ((rc = launch_deepz(ctx, true, kstats, c, gridg, threads, dz_meta_bytes(kstats), in, out, sg))) return rc;
+        if ((rc = launch_deepz(ctx, true, kstats, c, gridg, threads, metag, in, out, sg))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));

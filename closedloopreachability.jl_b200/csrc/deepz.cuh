@@ -293,7 +293,12 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeepzSmem& S = *reinterpret_cast<DeepzSmem*>(smem_raw);
     double* store = GLOBAL ? sp.workspace + (size_t)blockIdx.x * sp.cap
-                           : reinterpret_cast<double*>(smem_raw + dz_meta_bytes(STATS));
+                           : reinterpret_cast<double*>(smem_raw + sp.store_off);
+    // rows whose relaxation appended a generator, [pending | being written] x cell x word, and the position table
+    // (column of the current layout -> column of the next one; 0x8000: centre, 0xFFFF: unused), sized by the host
+    unsigned* const maskBase = reinterpret_cast<unsigned*>(smem_raw + dz_meta_bytes(STATS));
+    const int mS = sp.mask_stride, mWords = sp.mask_words, maskHalf = sp.tile_max * sp.mask_stride;
+    unsigned short* const colPosT = reinterpret_cast<unsigned short*>(maskBase + 2 * maskHalf);
     const int tid = threadIdx.x, NT = DZ_THREADS;
     const int lane = tid & 31, warp = tid >> 5, nWarps = NT >> 5;
     const int L = net->L;
@@ -316,7 +321,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
     const unsigned long long total_units =
         sp.pass == 0 ? (unsigned long long)in.N : (sp.pass == 1 ? st->n_retry : st->n_big);
     unsigned long long* cursor = sp.pass == 0 ? &st->next_cell : (sp.pass == 1 ? &st->next_retry : &st->next_big);
-    const int tileMax = min(CLR_TILE_CELLS_MAX, max(1, (sp.cap / 8) / stageW));   // staging takes 1/8 of the store at most
+    const int tileMax = min(min(CLR_TILE_CELLS_MAX, sp.tile_max), max(1, (sp.cap / 8) / stageW));   // staging takes 1/8 of the store at most
     unsigned long long pfFirst = 0;   // thread 0: prefetched tile
     int pfT = 0;
     if (tid == 0) {
@@ -354,6 +359,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             S.nCells = nc;
             S.more = nc > 0;
             S.peakNeed = 0.f;
+            S.peakCols = 0.f;
             if (nc > 0) {
                 int T = S.tileT;
                 if (sp.tile_cells <= 0 && sp.pass != 2) {
@@ -375,7 +381,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         const int stageOff = sp.cap - nCells * stageW;
         double* stage = store + stageOff;
         const int region = inplace ? stageOff : stageOff / 2;
-        const int capCols = min(region / P, CLR_NCOL_MAX);
+        const int capCols = min(region / P, sp.ncol_max);
         double* cur = store;
         double* oth = inplace ? store : store + region;
         if (tid < nCells) {
@@ -383,7 +389,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             S.cellId[tid] = sp.pass == 0 ? idx : (sp.pass == 1 ? sp.retry_list[idx] : sp.big_list[idx]);
             if (STATS) S.cellNear[tid] = 0;
         }
-        for (int i = tid; i < nCells * DZ_MASK_STRIDE; i += NT) (&S.mask[0][0][0])[i] = 0;
+        for (int i = tid; i < nCells * mS; i += NT) maskBase[i] = 0;
         if (needDead) for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) { S.deadMask[0][i] = 0; S.deadMask[1][i] = 0; }
         __syncthreads();
 
@@ -432,7 +438,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     S.colOff[0][keep] = total; S.colOff[1][keep] = total; S.nItems = 0;
                     S.kAct = in.kind == 0 ? S.layers[0].m : n;
                     if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
-                    if (keep > 0) S.peakNeed = (float)(total + 8) / (float)keep;
+                    if (keep > 0) { S.peakNeed = (float)(total + 8) / (float)keep; S.peakCols = (float)total / (float)keep; }
                 }
             }
             nCells = keep;
@@ -507,7 +513,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             for (int ci = warp; ci < nCells; ci += nWarps) {
                 const int cb = colOff[ci], w = S.wUsed[0][ci], wa = colOff[ci + 1] - cb;
                 for (int j = lane; j < wa; j += 32)
-                    S.colPos[cb + j] = j < w ? (unsigned short)((cb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
+                    colPosT[cb + j] = j < w ? (unsigned short)((cb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
             }
             __syncthreads();   // input store and position table complete
         }
@@ -522,14 +528,14 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             const DevLayer& Ly = S.layers[l];
             const int* offNxt = S.colOff[flip ^ 1];
             const unsigned short* wCur = S.wUsed[flip];
-            const unsigned (*pend)[DZ_MASK_STRIDE] = S.mask[flip];
-            unsigned (*fresh)[DZ_MASK_STRIDE] = S.mask[flip ^ 1];
+            const unsigned* pend = maskBase + flip * maskHalf;
+            unsigned* fresh = maskBase + (flip ^ 1) * maskHalf;
             if (STATS && Ly.net_layer >= 0 && tid < nCells) {
                 // generators entering this layer, as the reference counts them
                 const int cb = S.colOff[flip][tid], w = wCur[tid];
                 int nz = 0;
                 for (int j = 1; j < w; j++) nz += !((S.deadMask[flipD][(cb + j) >> 5] >> ((cb + j) & 31)) & 1u);
-                for (int ww = 0; ww < CLR_MASK_WORDS; ww++) nz += __popc(pend[tid][ww]);
+                for (int ww = 0; ww < mWords; ww++) nz += __popc(pend[tid * mS + ww]);
                 S.cellPin[tid][Ly.net_layer] = (unsigned short)nz;
                 S.cellUnst[tid][Ly.net_layer] = 0;
             }
@@ -537,7 +543,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             const bool relax = !(act == CLR_ACT_ID && !collapse);
             const int m = Ly.m, rowsP = clr_pad4(m), mw = (m + 31) >> 5;
             if (!(l == 0 && in.kind == 0))   // box cells enter with the first layer's product already applied
-                dz_gemm<KSREG, FULL>(Ly, cur, oth, P, nCols, S.kAct, S.colPos, !relax, inplace, warp, lane, nWarps, a);
+                dz_gemm<KSREG, FULL>(Ly, cur, oth, P, nCols, S.kAct, colPosT, !relax, inplace, warp, lane, nWarps, a);
             DZ_T(1);
             // Pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i].  In place this is safe
             // without another barrier: after the last group's barrier of the sweep every warp has read every column.
@@ -585,7 +591,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     for (int ci = 0; ci < nCells; ci++) {
                         int col = offNxt[ci] + wCur[ci];
                         for (int ww = 0; ww < mwPrev; ww++) {
-                            unsigned bits = pend[ci][ww];
+                            unsigned bits = pend[ci * mS + ww];
                             while (bits) {
                                 const int i = ww * 32 + __ffs(bits) - 1;
                                 bits &= bits - 1;
@@ -600,7 +606,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     }
                 }
             }
-            for (int i = tid; i < nCells * DZ_MASK_STRIDE; i += NT) (&fresh[0][0])[i] = 0;
+            for (int i = tid; i < nCells * mS; i += NT) fresh[i] = 0;
             if (tid == 0) S.kActNew = 0;
             // weights of the next layer (or of the first layer for the next tile) while the relaxation runs
             dz_load_a<KSREG>(S.layers[l + 1 < Lrun ? l + 1 : 0], warp, lane, nWarps, a);
@@ -611,7 +617,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) dNew[i] = 0;
                 __syncthreads();
                 for (int col = tid; col < nCols; col += NT) {
-                    const unsigned pos = S.colPos[col];
+                    const unsigned pos = colPosT[col];
                     if (pos != 0xFFFFu && ((dOld[col >> 5] >> (col & 31)) & 1u)) atomicOr(&dNew[(pos & 0x7FFFu) >> 5], 1u << (pos & 31));
                 }
                 flipD ^= 1;
@@ -721,7 +727,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                             }
                             if (unst) {
                                 stage[ci * stageW + r] = mm;
-                                atomicOr(&fresh[ci][r >> 5], 1u << (r & 31));
+                                atomicOr(&fresh[ci * mS + (r >> 5)], 1u << (r & 31));
                             }
                         }
                     }
@@ -738,7 +744,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 // no product follows the last layer: only the widths the output stage reads
                 if (tid < nCells) {
                     int u = 0;
-                    for (int ww = 0; ww < mw; ww++) u += __popc(fresh[tid][ww]);
+                    for (int ww = 0; ww < mw; ww++) u += __popc(fresh[tid * mS + ww]);
                     S.wUsed[flip ^ 1][tid] = (unsigned short)(collapse ? 2 : wCur[tid] + S.uPend[flip][tid]);
                     S.uPend[flip ^ 1][tid] = (unsigned short)u;
                     if (STATS && Ly.net_layer >= 0) S.cellUnst[tid][Ly.net_layer] = (unsigned short)u;
@@ -753,7 +759,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     const int ci = lane + 32 * h;
                     if (ci < nCells) {
                         int u = 0;
-                        for (int ww = 0; ww < mw; ww++) u += __popc(fresh[ci][ww]);
+                        for (int ww = 0; ww < mw; ww++) u += __popc(fresh[ci * mS + ww]);
                         uu[h] = u;
                         wu[h] = collapse ? 2 : wCur[ci] + S.uPend[flip][ci];
                         w[h] = max(max(colOff[ci + 1] - colOff[ci], wu[h] + u), minW);   // cells never shrink: they only move right
@@ -792,7 +798,10 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         S.nItems = nIt;
                         S.kAct = S.kActNew;
                         if (keep < nCells) dz_defer(sp, st, S.cellId, keep, nCells);
-                        if (keep > 0) S.peakNeed = fmaxf(S.peakNeed, (float)(total + 8) / (float)keep);
+                        if (keep > 0) {
+                            S.peakNeed = fmaxf(S.peakNeed, (float)(total + 8) / (float)keep);
+                            S.peakCols = fmaxf(S.peakCols, (float)total / (float)keep);
+                        }
                     }
                 } else if (warp == 1) {
                     if (lane < keep) { S.wUsed[flip ^ 1][lane] = (unsigned short)wu[0]; S.uPend[flip ^ 1][lane] = (unsigned short)uu[0]; }
@@ -809,11 +818,11 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     const int base = ci < 32 ? __shfl_sync(0xffffffffu, ub0, src) : __shfl_sync(0xffffffffu, ub1, src);
                     const int cb = colOff[ci], wa = colOff[ci + 1] - cb;
                     for (int j = lane; j < wa; j += 32)
-                        S.colPos[cb + j] = j < wuse ? (unsigned short)((nb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
+                        colPosT[cb + j] = j < wuse ? (unsigned short)((nb + j) | (j == 0 ? 0x8000 : 0)) : (unsigned short)0xFFFF;
                     if (listItems) {
                         int before = 0;
                         for (int ww = 0; ww < mw; ww++) {
-                            const unsigned bits = fresh[ci][ww];
+                            const unsigned bits = fresh[ci * mS + ww];
                             if ((bits >> lane) & 1u) {
                                 const int k = before + __popc(bits & ((1u << lane) - 1u));
                                 S.itemCol[base + k] = (unsigned short)(nb + wuse + k);
@@ -856,7 +865,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     const int cb = colOff[tid], w = S.wUsed[flip][tid];
                     int nz = 0;
                     for (int j = 1; j < w; j++) nz += !((dead[(cb + j) >> 5] >> ((cb + j) & 31)) & 1u);
-                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) nz += __popc(S.mask[flip][tid][ww]);
+                    for (int ww = 0; ww < mWords; ww++) nz += __popc(maskBase[flip * maskHalf + tid * mS + ww]);
                     S.cellPin[tid][Lt.net_layer] = (unsigned short)nz;
                     S.cellUnst[tid][Lt.net_layer] = 0;
                 }
@@ -884,7 +893,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 __syncthreads();
             }
             // ranks of the surviving output generators (remove_zero_columns); the position table is free now
-            unsigned short* colRank = S.colPos;
+            unsigned short* colRank = colPosT;
             int* rank0 = S.colOff[flip ^ 1];              // rank of a cell's first pending generator
             if (needDead) {
                 if (tid < nCells) {
@@ -896,7 +905,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         colRank[cb + j] = dd ? (unsigned short)0xFFFF : (unsigned short)(k++);
                     }
                     int u = 0;
-                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[flip][tid][ww]);
+                    for (int ww = 0; ww < mWords; ww++) u += __popc(maskBase[flip * maskHalf + tid * mS + ww]);
                     rank0[tid] = k;
                     if (STATS) atomicMax(&S.sMaxP, tailCollapse ? 1 : k + u);      // a one-row map returns a single generator
                     if (STATS && out.keep_cap > 0) {
@@ -910,7 +919,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 const int ci = it / mOut, r = it - ci * mOut;
                 const int cb = colOff[ci], w = S.wUsed[flip][ci];
                 const double* y = cur + cb * P + r;
-                const unsigned mwv = S.mask[flip][ci][r >> 5];
+                const unsigned mwv = (r >> 5) < mWords ? maskBase[flip * maskHalf + ci * mS + (r >> 5)] : 0u;
                 const bool pend = !fuse && ((mwv >> (r & 31)) & 1u);     // this row's own appended generator mu * e_r
                 const double mu = pend ? stage[ci * stageW + r] : 0.0;
                 double c = y[0], lo, hi;
@@ -922,7 +931,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         lo = c; hi = c;
                         for (int j = 1; j < w; j++) { double av = fabs(y[j * P]); lo -= av; hi += av; }
                         for (int ww = 0; ww < mwN; ww++) {
-                            unsigned bits = S.mask[flip][ci][ww];
+                            unsigned bits = maskBase[flip * maskHalf + ci * mS + ww];
                             while (bits) {
                                 const int i = ww * 32 + __ffs(bits) - 1;
                                 bits &= bits - 1;
@@ -934,7 +943,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         double rad = 0.0;
                         for (int j = 1; j < w; j++) rad += fabs(y[j * P]);
                         for (int ww = 0; ww < mwN; ww++) {
-                            unsigned bits = S.mask[flip][ci][ww];
+                            unsigned bits = maskBase[flip * maskHalf + ci * mS + ww];
                             while (bits) {
                                 const int i = ww * 32 + __ffs(bits) - 1;
                                 bits &= bits - 1;
@@ -967,9 +976,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         if (k != 0xFFFF && k < out.keep_cap) g[(size_t)k * mOut] = y[j * P];
                     }
                     int k0 = rank0[ci], u = 0;
-                    for (int ww = 0; ww < CLR_MASK_WORDS; ww++) u += __popc(S.mask[flip][ci][ww]);
+                    for (int ww = 0; ww < mWords; ww++) u += __popc(maskBase[flip * maskHalf + ci * mS + ww]);
                     int rank = __popc(mwv & ((1u << (r & 31)) - 1u));
-                    for (int ww = 0; ww < (r >> 5); ww++) rank += __popc(S.mask[flip][ci][ww]);
+                    for (int ww = 0; ww < (r >> 5); ww++) rank += __popc(maskBase[flip * maskHalf + ci * mS + ww]);
                     for (int k = 0; k < u; k++)
                         if (k0 + k < out.keep_cap) g[(size_t)(k0 + k) * mOut] = (pend && k == rank) ? mu : 0.0;
                 }
@@ -996,6 +1005,12 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 // columns and staging both scale with the number of cells
                 const float perCell = S.peakNeed * margin * (float)P * (inplace ? 1.f : 2.f) + (float)stageW;
                 int T = (int)((float)(sp.cap - 16 * P) / perCell);
+                if (sp.grow_cols > 0 && sp.pass == 0) {
+                    // sigmoid / tanh layers: the growth of a cell is known, not estimated -- the largest tile whose columns,
+                    // 8 columns of slack and staging fit exactly (wide cells: one more cell per tile is a large step)
+                    const float per = S.peakCols * (float)P * (inplace ? 1.f : 2.f) + (float)stageW;
+                    T = max(T, (int)((float)(sp.cap - 8 * P * (inplace ? 1 : 2)) / per));
+                }
                 S.tileT = max(1, min(T, tileMax));
             }
             if (STATS) atomicAdd(&st->tiles, 1ull);

@@ -38,13 +38,19 @@ struct DeepzSched {
     int cap;                  // doubles of column store (+ staging) per CTA
     int inplace;              // 1: layer products run in place (every warp owns at most one row block)
     int grow_cols;            // generators every cell is known to gain (sigmoid / tanh layers append one per neuron)
+    // tile metadata sized for the launch at hand (dz_geom on the host): the appended-generator masks and the position table
+    // live behind DeepzSmem, the column store behind them
+    int mask_words;           // 32-bit words of a cell's row mask (ceil(max rows / 32))
+    int mask_stride;          // words between the masks of two cells (odd: conflict-free column reads)
+    int tile_max;             // cells a tile may hold (<= CLR_TILE_CELLS_MAX)
+    int ncol_max;             // columns a tile may hold (<= CLR_NCOL_MAX); the position table has ncol_max + 32 entries
+    int store_off;            // byte offset of the column store in dynamic shared memory
     int fuse_tail;            // 1: the last layer (Id, at most 4 inputs and rows) is applied column by column in the output stage
     long long* retry_list;
     long long* big_list;
     double* workspace;        // pass 2: gridDim.x * cap doubles
 };
 
-#define DZ_MASK_STRIDE (CLR_MASK_WORDS + 1)   // odd row stride: the lanes of a warp read one word of 32 cells without bank conflicts
 #define DZ_ITEMS_MAX 384   // pending generators listed per tile (more: the slow walk over the masks)
 
 struct DeepzSmem {
@@ -55,14 +61,13 @@ struct DeepzSmem {
     int sMaxP;
     long long firstIdx;
     float peakNeed;
+    float peakCols;                           // columns per cell at the widest layer of the tile, without the slack
     int colOff[2][CLR_TILE_CELLS_MAX + 1];    // cell offsets of the current and of the next layout
     unsigned short wUsed[2][CLR_TILE_CELLS_MAX];   // columns of a cell that hold data (centre + generators), per layout
     unsigned short uPend[2][CLR_TILE_CELLS_MAX];   // generators of a cell still pending (appended by the last relaxation)
     int nItems;                                    // pending generators of the tile listed in item*
     unsigned short itemCol[DZ_ITEMS_MAX], itemCell[DZ_ITEMS_MAX], itemRow[DZ_ITEMS_MAX];
     long long cellId[CLR_TILE_CELLS_MAX];
-    unsigned mask[2][CLR_TILE_CELLS_MAX][DZ_MASK_STRIDE];   // rows whose relaxation appended a generator: [pending | being written]
-    unsigned short colPos[CLR_NCOL_MAX];      // column of the current layout -> column of the next one (0x8000: centre, 0xFFFF: unused)
     unsigned deadMask[2][CLR_NCOL_MAX / 32];  // generators the reference's remove_zero_columns has dropped
     double hlo[CLR_HULL_MAX], hhi[CLR_HULL_MAX];
     unsigned long long sPin[CLR_MAX_LAYERS], sUnst[CLR_MAX_LAYERS], sNear;
