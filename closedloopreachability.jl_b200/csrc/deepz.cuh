@@ -330,7 +330,10 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             int guessCols = in.kind == 0 ? in.n + 1 : 8;
             t0 = (sp.cap / (inplace ? 1 : 2)) / ((guessCols * 2 + 8 + sp.grow_cols) * P);
             if (sp.pass != 0) t0 = max(1, t0 / 4);
-            unsigned long long fair = (total_units + 2ull * gridDim.x - 1) / (2ull * gridDim.x);
+            // small calls (the whole call fits one tile per CTA): exactly one tile each -- a tile costs its latency chain
+            // whatever its size; otherwise two tiles per CTA and round, so that the tail balances
+            const unsigned long long one = (total_units + gridDim.x - 1) / gridDim.x;
+            unsigned long long fair = one <= (unsigned long long)t0 ? one : (total_units + 2ull * gridDim.x - 1) / (2ull * gridDim.x);
             if ((unsigned long long)t0 > fair) t0 = (int)(fair < 1 ? 1 : fair);
         }
         if (sp.pass == 2) t0 = 1;
