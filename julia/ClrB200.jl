@@ -111,6 +111,21 @@ function controller_forward_boxes(ctx::Context, dnet::DeviceNetwork, Zs::Abstrac
 end
 
 """
+Same for cells in the padded layout `project_oa_batch` returns (centres n x N, generators n x cap x N, counts): the cells of
+control period k + 1 without building a `Zonotope` per chain (src/solve.jl:183-195).
+"""
+function controller_forward_boxes(ctx::Context, dnet::DeviceNetwork, C::Matrix{Float64}, G::Array{Float64,3}, ncols::Vector{Int32},
+                                  pp::PrePost, m::Integer)
+    n, N = size(C); cap = size(G, 2)
+    lo = Matrix{Float64}(undef, m, N); hi = similar(lo)
+    check(ctx, ccall((:clr_deepz_zonotopes_padded, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32, Ref{PrePost},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Int32, Int32),
+                     ctx.h, dnet.h, n, N, C, G, ncols, cap, pp, lo, hi, C_NULL, C_NULL, C_NULL, 0, 2))
+    return lo, hi
+end
+
+"""
 `TaylorModelReconstructor(box=false)` (src/setops.jl:84-101) for all cells of the last `keep_cap > 0` run at once:
 `Z0 = _reduce_order(U0, 2; force_reduction=true)`.  Returns the centres (m x N) and the generators (m x 2m x N);
 cell i's `M = G[:, 1:m, i]` and diagonal `D = G[:, m+1:2m, i]` are what the loop at src/setops.jl:96-101 reads.
