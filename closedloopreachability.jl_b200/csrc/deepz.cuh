@@ -1004,7 +1004,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         // ---- adapt the tile size to the growth just seen ---------------------------------------------------------------
         if (tid == 0) {
             if (sp.tile_cells <= 0 && sp.pass != 2) {
-                const float margin = sp.pass == 0 ? 1.0625f : 1.5f;
+                const float margin = sp.pass == 0 ? DZ_MARGIN : 1.5f;
                 // columns and staging both scale with the number of cells
                 const float perCell = S.peakNeed * margin * (float)P * (inplace ? 1.f : 2.f) + (float)stageW;
                 int T = (int)((float)(sp.cap - 16 * P) / perCell);

@@ -85,4 +85,7 @@ __host__ __device__ inline size_t dz_meta_bytes(bool stats) {
 #ifndef DZ_NB
 #define DZ_NB 4         // column blocks per group of the layer product (one barrier per group in place)
 #endif
+#ifndef DZ_MARGIN
+#define DZ_MARGIN 1.0625f   // head-room of the adaptive tile size over the growth seen so far (main pass)
+#endif
 #define DZ_THREADS 512   // 16 warps, always (4 per SM sub-partition: 128 registers per thread)
