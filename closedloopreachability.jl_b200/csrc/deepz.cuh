@@ -405,9 +405,11 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             for (int it = tid; it < nCells * n; it += NT) {
                 const int ci = it / n, d = it - ci * n;
                 const unsigned long long g = (unsigned long long)(in.cell_begin + S.cellId[ci]);
+                const unsigned long long sd = (unsigned long long)in.stride[d];   // can exceed 2^32 even when g does not
                 int k;
-                if ((g >> 32) == 0) k = (int)(((unsigned)g / (unsigned)in.stride[d]) % (unsigned)in.part[d]);
-                else k = (int)((g / (unsigned long long)in.stride[d]) % (unsigned long long)in.part[d]);
+                if (sd > g) k = 0;
+                else if ((g >> 32) == 0) k = (int)(((unsigned)g / (unsigned)sd) % (unsigned)in.part[d]);
+                else k = (int)((g / sd) % (unsigned long long)in.part[d]);
                 tmpC[it] = __ldg(in.centers + in.base[d] + k);
                 tmpR[it] = __ldg(in.radii + in.base[d] + k);
             }
