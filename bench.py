@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true", help="skip the simulate() rollout line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traj", type=int, default=1000000)
+    ap.add_argument("--no-regimes", action="store_true", help="skip the mixed / dense regime lines")
+    ap.add_argument("--shards", default="cyclic", choices=["cyclic", "equal", "cost"],
+                    help="N > 1: block-cyclic shards (default), contiguous equal counts, or contiguous cost-weighted ranges")
     return ap.parse_args()
 
 
@@ -123,29 +126,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic(regime):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one main-pass launch of this workload (ncu --set full capture
-    committed under profiles/; the boxes written by the launch stay in the 126 MB L2 at this size)."""
-    try:
-        if regime != "stable":
-            return None
-        with open(os.path.join(ROOT, "profiles", "r01", "ncu_deepz_bench_launch.json")) as fh:
-            return json.load(fh)["traffic"]
-    except Exception:
-        return None
-
-
 def workload(args, world):
-    """C4: box [c0-s, c0+s]^6 split [10]^6; with N ranks the box is N times longer in the last (slowest)
-    dimension and split 10 N times there, so every rank owns 10^6 cells of identical size."""
+    """C4: box [c0-s, c0+s]^6 split [10]^5 x [10 N]: with N ranks the SAME box is split N times finer in the last (slowest)
+    dimension -- the way a verification run that needs more precision grows -- so the job has N x 10^6 cells of about
+    the same cost each (round 1 made the box N times longer instead: its far end is costlier per cell, which put
+    8 % of 'scaling loss' into the workload itself)."""
     from clr_b200 import workloads
     from clr_b200.splitters import split_box
     net = workloads.synthetic_relu_net()
     c0, s = {"dense": (0.0, 1.0), "mixed": (0.3, 0.1), "stable": (0.3, 0.01)}[args.regime]
     k = args.cells_per_dim
-    lo = [c0 - s] * 6
-    hi = [c0 + s] * 5 + [c0 - s + 2 * s * world]
-    grid = split_box(lo, hi, [k] * 5 + [k * world])
+    grid = split_box([c0 - s] * 6, [c0 + s] * 6, [k] * 5 + [k * world])
     return net, grid
 
 
@@ -198,60 +189,84 @@ def run_reference(args):
     emit(line)
 
 
-def run_ours(args):
+def hw_utilisation(regime):
+    """Hardware counters of the main-pass launch of this workload from the committed ncu --set full capture (not measured
+    in this run: ncu replays a kernel ~40 times and a number taken under a profiler is never a bench value)."""
+    for rel in (os.path.join("profiles", "r02", f"ncu_deepz_{regime}.json"), os.path.join("profiles", "r02", "ncu_deepz_stable.json"),
+                os.path.join("profiles", "r01", "ncu_deepz_bench_launch.json")):
+        try:
+            with open(os.path.join(ROOT, rel)) as fh:
+                d = json.load(fh)
+            if regime not in rel and regime != "stable":
+                continue
+            return {"dmma_pipe_active_pct": d.get("dmma_pipe_active_pct"), "issue_active_pct": d.get("issue_active_pct"),
+                    "fp64_pipe_pct": d.get("fp64_pipe_pct"), "traffic_bytes_per_launch": d.get("traffic"),
+                    "cells_in_capture": d.get("cells"), "source": f"committed ncu capture {rel} (not measured in this run)"}
+        except Exception:
+            continue
+    return None
+
+
+def measure_regime(args, regime, steps, warmup, ctx, dev, stream, flush, rank, world, fp64_peak, e2e_steps):
+    """One regime of C4 on this rank's shard: device-resident throughput (CUDA events on the library's stream, L2 flushed
+    between steps), per-pass times, algorithmic FLOPs, and the end-to-end number through the host-buffer API."""
     import torch
-    import clr_b200
-    from clr_b200 import _lib, parallel, runtime, workloads
-    rank, local, world = dist_env()
     import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    ctx = runtime.Context(local)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    net, grid = workload(args, world)
+    from clr_b200 import _lib, parallel, runtime
+    a2 = argparse.Namespace(**vars(args))
+    a2.regime = regime
+    net, grid = workload(a2, world)
     dn = ctx.upload(net)
-    b, cnt = parallel.shard_range(len(grid), rank, world)
     m = 1
     pp = runtime.PrePostArg(None, None)
-
-    # inputs resident in HBM: the split tables; outputs: boxes + hull, device resident
     cc = torch.from_numpy(np.concatenate(grid.centers)).to(dev)
     rr = torch.from_numpy(np.concatenate(grid.radii)).to(dev)
+    # shards: block-cyclic by default (rank r takes the blocks r, r + N, ... of 1024 cells: every share is spread over the
+    # whole split, so the ranks take the same time without a cost model); --shards equal / cost give contiguous ranges
+    cost, blk, stride = None, 0, 0
+    if world > 1 and args.shards == "cyclic":
+        blk, stride = 1024, 1024 * world
+        nb = (len(grid) + blk - 1) // blk
+        cnt = sum(min(blk, len(grid) - j * blk) for j in range(rank, nb, world))
+        b = rank * blk
+    else:
+        if world > 1 and args.shards == "cost":
+            bounds, cost = parallel.balanced_bounds(ctx, dn, grid, world)
+        else:
+            bounds = [parallel.shard_range(len(grid), r, world)[0] for r in range(world)] + [len(grid)]
+        b, cnt = bounds[rank], bounds[rank + 1] - bounds[rank]
     d_lo = torch.empty((cnt, m), dtype=torch.float64, device=dev)
     d_hi = torch.empty((cnt, m), dtype=torch.float64, device=dev)
     d_hl = torch.empty(m, dtype=torch.float64, device=dev)
     d_hh = torch.empty(m, dtype=torch.float64, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     torch.cuda.synchronize()
 
     def step_dev():
-        ctx.deepz_boxgrid_dev(dn, 6, grid.partition, cc, rr, b, cnt, pp, d_lo, d_hi, d_hl, d_hh)
+        ctx.deepz_boxgrid_dev(dn, 6, grid.partition, cc, rr, b, cnt, pp, d_lo, d_hi, d_hl, d_hh, block=blk, stride=stride)
 
     # algorithmic FLOPs of one step (statistics run, untimed)
     st = _lib.Stats()
-    ctx.deepz_boxgrid_dev(dn, 6, grid.partition, cc, rr, b, cnt, pp, d_lo, d_hi, d_hl, d_hh, stats=st)
+    ctx.deepz_boxgrid_dev(dn, 6, grid.partition, cc, rr, b, cnt, pp, d_lo, d_hi, d_hl, d_hh, stats=st, block=blk, stride=stride)
     ctx.synchronize()
     flops_step = st.flops
     p_in = [st.sum_p_in[l] / cnt for l in range(5)]
 
     ctx.set_profiling(True)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_dev()
     ctx.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     launches0 = ctx.launch_count
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     pass_ms = np.zeros(3)
     retried = big = 0
     wall0 = time.perf_counter()
-    for s in range(args.steps):
+    for s in range(steps):
         with torch.cuda.stream(stream):
             flush.zero_()                       # L2 flush between timed iterations (not timed)
             ev0[s].record(stream)
@@ -268,26 +283,27 @@ def run_ours(args):
     dev_ms = sum(a.elapsed_time(bb) for a, bb in zip(ev0, ev1))
     if world > 1:
         dist.barrier()
-    t_ms = parallel.max_over_ranks(dev_ms, device=dev)
-    total_cells = parallel.sum_over_ranks(cnt, device=dev)
-    value = total_cells * args.steps / (t_ms * 1e-3)
-    # final gather of the per-GPU hulls over NCCL (the only communication of the path)
-    hl, hh = parallel.gather_hull(d_hl, d_hh)
+    rank_ms = parallel.gather_scalars(dev_ms / steps, device=dev)        # per-rank ms per step
+    rank_flops = parallel.gather_scalars(flops_step, device=dev)
+    rank_cells = parallel.gather_scalars(cnt, device=dev)
+    t_ms = max(rank_ms) * steps
+    total_cells = sum(rank_cells)
+    value = total_cells * steps / (t_ms * 1e-3)
+    hl, hh = parallel.gather_hull(d_hl, d_hh)   # final gather of the per-GPU hulls over NCCL (the only communication)
     hull = [float(hl[0]), float(hh[0])]
 
     # ---- end to end: host buffers through the public API (blocking call) -------------------------------
     out_lo = torch.empty((cnt, m), dtype=torch.float64).pin_memory().numpy()
     out_hi = torch.empty((cnt, m), dtype=torch.float64).pin_memory().numpy()
-    e2e_steps = max(3, min(args.steps, 10))
     ctx.deepz_boxgrid(dn, grid.partition, grid.centers, grid.radii, cell_begin=b, cell_count=cnt, stats=False,
-                      out_lo=out_lo, out_hi=out_hi)
+                      out_lo=out_lo, out_hi=out_hi, block=blk, stride=stride)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ctx.deepz_boxgrid(dn, grid.partition, grid.centers, grid.radii, cell_begin=b, cell_count=cnt, stats=False,
-                          out_lo=out_lo, out_hi=out_hi)
+                          out_lo=out_lo, out_hi=out_hi, block=blk, stride=stride)
     torch.cuda.synchronize()
     e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, device=dev)
     tab_bytes = 2 * 8 * int(np.sum(grid.partition))
@@ -296,30 +312,83 @@ def run_ours(args):
            "note": "clr_deepz_boxgrid with host buffers: H2D of the split tables, D2H of every cell's box, blocking"}
     assert np.array_equal(out_lo, d_lo.cpu().numpy())
 
-    # ---- roofline of the dominant kernel (main-pass deepz_kernel, or the big-cell pass in the dense regime) ----
+    # ---- roofline: WHOLE step (every pass, the pilot and the host gaps between them), per GPU --------------------------
+    ms_step = t_ms / steps
+    flops_per_gpu = sum(rank_flops) / world
+    ach = flops_per_gpu / (ms_step * 1e-3) / 1e12
     dom = int(np.argmax(pass_ms))
-    dom_ms = pass_ms[dom] / args.steps
-    ach = flops_step / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": ["deepz_kernel (main pass, smem store)", "deepz_kernel (retry pass)",
-                                              "deepz_kernel (big-cell pass, global store)"][dom],
-                "achieved": ach, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": ach / DMMA_PEAK_TFLOPS,
-                "traffic": ncu_traffic(args.regime),
-                "peak_source": "FP64 mma.sync (DMMA) issue peak measured on this pool's B200 "
-                               "(profiles/microbench/r01_dmma_bench_b200.txt; cuBLAS DGEMM 8192^3 = 35.5); "
-                               "MEASURED_PEAKS.json has no FP64 entry",
-                "algorithmic_flops_per_step": flops_step, "kernel_ms_per_step": dom_ms,
-                "pass_ms_per_step": (pass_ms / args.steps).tolist(), "mean_generators_in": p_in,
-                "cells_retried": int(retried), "cells_big": int(big)}
+    dom_ms = pass_ms[dom] / steps
+    hw = hw_utilisation(regime)
+    roofline = {"bound": "tensor", "achieved": ach, "peak": fp64_peak["value"], "unit": "TFLOP/s", "frac": ach / fp64_peak["value"],
+                "traffic": hw["traffic_bytes_per_launch"] if hw else None,
+                "traffic_source": hw["source"] if hw else None,
+                "what": "achieved = algorithmic FLOPs of one step (per GPU: 2 m n (p + 1) per layer and cell, p counted by the "
+                        "kernel's statistics run) / ms_per_step -- the whole step, all passes",
+                "peak_source": fp64_peak["source"],
+                "algorithmic_flops_per_step": flops_per_gpu,
+                "dominant_kernel": {"name": ["deepz_kernel (main pass, smem store)", "deepz_kernel (retry pass)",
+                                             "deepz_kernel (big-cell pass, global store)"][dom],
+                                    "ms_per_step": dom_ms, "share_of_step": dom_ms / ms_step,
+                                    "algorithmic_tflops_if_it_did_all_the_work": flops_step / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else None},
+                "pass_ms_per_step": (pass_ms / steps).tolist(), "mean_generators_in": p_in,
+                "cells_retried": int(retried), "cells_big": int(big),
+                "hardware_utilisation": hw}
+    return {"value": value, "ms_per_step": ms_step, "rank_ms_per_step": rank_ms, "rank_cells": [int(c) for c in rank_cells],
+            "rank_algorithmic_flops": rank_flops, "shard_cost_model": cost, "clocks": clocks, "e2e": e2e, "launches": int(launches),
+            "roofline": roofline, "wall": wall, "hull": hull, "cnt": cnt, "net": net, "grid": grid, "steps": steps, "warmup": warmup}
 
-    line = {"metric": METRIC, "value": value, "unit": "propagations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+
+def run_ours(args):
+    import torch
+    import clr_b200
+    from clr_b200 import parallel, runtime, workloads
+    rank, local, world = dist_env()
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = runtime.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    # FP64 tensor roofline denominator, measured on this device in this run (MEASURED_PEAKS.json has no FP64 entry)
+    live = ctx.measure_fp64_peak(30.0)
+    fp64_peak = {"value": live, "source": f"FP64 mma.sync (DMMA) issue peak measured in this run on this GPU (clr_measure_fp64_peak, "
+                                           f"{live:.2f} TFLOP/s); committed microbenchmark: {DMMA_PEAK_TFLOPS} (profiles/microbench/"
+                                           "r01_dmma_bench_b200.txt; cuBLAS DGEMM 8192^3 = 35.5); MEASURED_PEAKS.json has no FP64 entry"}
+    e2e_steps = max(3, min(args.steps, 10))
+    main = measure_regime(args, args.regime, args.steps, args.warmup, ctx, dev, stream, flush, rank, world, fp64_peak, e2e_steps)
+    net, grid, cnt = main["net"], main["grid"], main["cnt"]
+
+    line = {"metric": METRIC, "value": main["value"], "unit": "propagations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C4 synthetic scaling: {cnt} box cells per GPU (split [10]^5 x [10 N] of a 6-dim box), "
+            "config": {"workload": f"C4 synthetic scaling: {len(grid) // world} box cells per GPU (split [10]^5 x [10 N] of a 6-dim box), "
                                    f"6->100x4->1 ReLU network (seed 4), Float64 DeepZ, regime={args.regime}",
-                       "cells_per_gpu": cnt, "regime": args.regime, "l2": "256 MB buffer written between timed steps",
-                       "hull": hull},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "wall_s_timed_region": wall}
+                       "cells_per_gpu": len(grid) // world, "regime": args.regime, "l2": "256 MB buffer written between timed steps",
+                       "hull": main["hull"],
+                       "shards": "one shard" if world == 1 else
+                                 {"cyclic": "block-cyclic: rank r takes the blocks r, r + N, ... of 1024 cells",
+                                  "equal": "contiguous cell-id ranges of equal counts",
+                                  "cost": "contiguous cell-id ranges, boundaries weighted by a pilot's per-cell cost"}[args.shards]},
+            "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["launches"], "roofline": main["roofline"],
+            "wall_s_timed_region": main["wall"],
+            "per_rank": {"ms_per_step": main["rank_ms_per_step"], "cells": main["rank_cells"],
+                         "algorithmic_flops_per_step": main["rank_algorithmic_flops"], "shard_cost_model": main["shard_cost_model"]}}
+
+    # ---- the other regimes of SURVEY 8d (the box as is = "dense", and the intermediate one), same split, fewer steps -----
+    if not args.no_regimes:
+        line["regimes"] = {}
+        for reg in ("stable", "mixed", "dense"):
+            if reg == args.regime:
+                continue
+            r = measure_regime(args, reg, 3, 3, ctx, dev, stream, flush, rank, world, fp64_peak, 3)
+            line["regimes"][reg] = {"value": r["value"], "unit": "propagations/s", "ms_per_step": r["ms_per_step"], "steps": 3,
+                                    "warmup": 3, "e2e": r["e2e"]["value"], "rank_ms_per_step": r["rank_ms_per_step"],
+                                    "roofline": {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "algorithmic_flops_per_step",
+                                                                                "pass_ms_per_step", "mean_generators_in", "cells_retried",
+                                                                                "cells_big", "hardware_utilisation")},
+                                    "clocks": r["clocks"]}
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(net, grid)

@@ -17,10 +17,12 @@ MAX_LAYERS = 32
 SYMBOLS = [
     "clr_create", "clr_destroy", "clr_last_error", "clr_stream", "clr_synchronize", "clr_launch_count",
     "clr_device_alloc", "clr_device_free", "clr_memcpy_h2d", "clr_memcpy_d2h", "clr_set_tile_cells",
-    "clr_set_profiling", "clr_last_pass_info", "clr_set_reorder",
-    "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_zonotopes", "clr_deepz_zonotopes_padded",
+    "clr_set_profiling", "clr_last_pass_info", "clr_set_reorder", "clr_measure_fp64_peak", "clr_last_device_error",
+    "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_boxgrid_cyclic", "clr_deepz_zonotopes", "clr_deepz_zonotopes_padded",
     "clr_deepz_fetch_zonotopes", "clr_deepz_fetch_reduced", "clr_project_oa", "clr_forward_points", "clr_rollout",
     "clr_plant_compile", "clr_plant_free", "clr_rollout_plant",
+    "clr_create_multi", "clr_destroy_multi", "clr_multi_size", "clr_multi_ctx", "clr_multi_last_error",
+    "clr_multi_net_upload", "clr_multi_net_free", "clr_multi_deepz_boxgrid", "clr_multi_rollout",
 ]
 
 
@@ -77,12 +79,18 @@ def lib():
     L.clr_set_profiling.restype = i32
     L.clr_last_pass_info.argtypes = [vp, vp, vp, vp]
     L.clr_last_pass_info.restype = i32
+    L.clr_last_device_error.argtypes = [vp, C.POINTER(i32)]
+    L.clr_last_device_error.restype = i32
+    L.clr_measure_fp64_peak.argtypes = [vp, dbl, C.POINTER(dbl)]
+    L.clr_measure_fp64_peak.restype = i32
     L.clr_net_upload.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(vp)]
     L.clr_net_upload.restype = i32
     L.clr_net_free.argtypes = [vp]
     L.clr_net_free.restype = None
     L.clr_deepz_boxgrid.argtypes = [vp, vp, i32, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i32, i32]
     L.clr_deepz_boxgrid.restype = i32
+    L.clr_deepz_boxgrid_cyclic.argtypes = [vp, vp, i32, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, i32, i32]
+    L.clr_deepz_boxgrid_cyclic.restype = i32
     L.clr_deepz_zonotopes.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
     L.clr_deepz_zonotopes.restype = i32
     L.clr_deepz_zonotopes_padded.argtypes = [vp, vp, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32]
@@ -105,5 +113,24 @@ def lib():
     L.clr_rollout_plant.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, dbl, dbl, dbl, i32, dbl, dbl, i32, i32, vp, vp, vp, vp, i32,
                                     vp, vp, vp, i32]
     L.clr_rollout_plant.restype = i32
+    L.clr_create_multi.argtypes = [vp, i32, C.POINTER(vp)]
+    L.clr_create_multi.restype = i32
+    L.clr_destroy_multi.argtypes = [vp]
+    L.clr_destroy_multi.restype = None
+    L.clr_multi_size.argtypes = [vp]
+    L.clr_multi_size.restype = i32
+    L.clr_multi_ctx.argtypes = [vp, i32]
+    L.clr_multi_ctx.restype = vp
+    L.clr_multi_last_error.argtypes = [vp]
+    L.clr_multi_last_error.restype = C.c_char_p
+    L.clr_multi_net_upload.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(vp)]
+    L.clr_multi_net_upload.restype = i32
+    L.clr_multi_net_free.argtypes = [vp]
+    L.clr_multi_net_free.restype = None
+    L.clr_multi_deepz_boxgrid.argtypes = [vp, vp, i32, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.clr_multi_deepz_boxgrid.restype = i32
+    L.clr_multi_rollout.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i32, vp, vp, dbl, dbl, dbl, i32, dbl, dbl, i32, i32,
+                                    vp, vp, vp, vp]
+    L.clr_multi_rollout.restype = i32
     _lib = L
     return L

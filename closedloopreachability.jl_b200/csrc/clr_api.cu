@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <dlfcn.h>
@@ -47,19 +48,25 @@ struct Compiled {            // one (network, pre/post-processing) pair on the d
     int stored_width = 0;
     int point_code = 1;
     int inplace = 1;
+    std::vector<HostLayer> layers_folded;     // the layer list this image was built from
+    Compiled* perm = nullptr;                 // the same network with reordered neurons (see compile_net_reordered)
+    std::vector<unsigned char> pilot_key;     // the split `perm` was derived for: the pilot is skipped while it stays the same
+    int pilot_peak_cols = 0;                  // columns per cell at the widest layer, seen by that pilot (picks the wide relaxation)
 };
 
 }  // namespace
 
 struct clr_net {
     clr_ctx* ctx;
+    int device = 0;                           // kept apart from ctx: clr_net_free must work after clr_destroy(ctx)
     int L;
     std::vector<int> dims, act;
     std::vector<std::vector<double>> W, b;
-    Compiled* compiled = nullptr;
-    Compiled* compiled_perm = nullptr;        // the same network with reordered neurons (see compile_net_reordered)
-    std::vector<HostLayer> layers_folded;    // layer list of `compiled`
+    // device images per (pre/post-processing, input dimension), most recently used first: DeepZ and rollout calls with
+    // different processing alternate without recompiling (and without the device synchronisation a cudaFree implies)
+    std::vector<Compiled*> variants;
 };
+#define CLR_NET_VARIANTS 4
 
 // a run-time compiled plant right-hand side (NVRTC -> cubin -> cudaLibrary), one module per evaluator code, built on demand
 struct clr_plant {
@@ -104,6 +111,7 @@ struct clr_ctx {
     int64_t keep_cells = 0;
     int keep_cap = 0, keep_m = 0;
     int* d_err = nullptr;
+    int* d_chk = nullptr;                // [max, min] generator counts of device-resident batches
     // pilot run of the neuron reordering (see reorder_for_grid)
     DevCallState* d_state2 = nullptr;
     int* d_live = nullptr;
@@ -171,17 +179,41 @@ __global__ void fill_hull_kernel(double* hull, int m) {
     if (i < m) { hull[i] = INFINITY; hull[m + i] = -INFINITY; }
 }
 
-__global__ void max_cols_kernel(const long long* col_off, long long N, int* out) {
-    int best = 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        int p = (int)(col_off[i + 1] - col_off[i]);
-        best = p > best ? p : best;
+// clr_measure_fp64_peak: 8 independent DMMA chains per warp, operands in registers
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a0, double b0) {
+    double d[8][2];
+#pragma unroll
+    for (int c = 0; c < 8; c++) { d[c][0] = threadIdx.x; d[c][1] = c; }
+    const double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(d[c][0]), "+d"(d[c][1]) : "d"(a), "d"(b));
     }
-    atomicMax(out, best);
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) s += d[c][0] + d[c][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// generator counts of device-resident zonotope batches: out[0] = max, out[1] = min (a negative minimum = decreasing offsets)
+__global__ void max_cols_kernel(const long long* col_off, const int* ncols, long long N, int* out) {
+    int best = 0, worst = 0x7fffffff;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const long long d = col_off ? col_off[i + 1] - col_off[i] : (long long)ncols[i];
+        const int p = d > 0x7fffffffLL ? 0x7fffffff : (d < -0x7fffffffLL ? -0x7fffffff : (int)d);
+        best = p > best ? p : best;
+        worst = p < worst ? p : worst;
+    }
+    atomicMax(&out[0], best);
+    atomicMin(&out[1], worst);
+    if (col_off && blockIdx.x == 0 && threadIdx.x == 0 && col_off[0] != 0) atomicMin(&out[1], -1);
 }
 
 void free_compiled(Compiled* c) {
     if (!c) return;
+    free_compiled(c->perm);
     for (void* p : c->allocs) cudaFree(p);
     delete c;
 }
@@ -399,32 +431,37 @@ int compile_layers(clr_ctx* ctx, const std::vector<HostLayer>& layers, int n_in,
 
 int compile_net(clr_ctx* ctx, clr_net* net, const clr_prepost* pp, int n_in, Compiled** outc) {
     std::vector<unsigned char> key = prepost_key(net, pp, n_in);
-    if (net->compiled && net->compiled->key == key) { *outc = net->compiled; return 0; }
+    for (size_t i = 0; i < net->variants.size(); i++)
+        if (net->variants[i]->key == key) {
+            Compiled* c = net->variants[i];
+            net->variants.erase(net->variants.begin() + (long)i);
+            net->variants.insert(net->variants.begin(), c);
+            *outc = c;
+            return 0;
+        }
     std::vector<HostLayer> layers;
     int rc = fold_layers(ctx, net, pp, n_in, layers);
     if (rc) return rc;
     Compiled* c = nullptr;
     if ((rc = compile_layers(ctx, layers, n_in, key, &c))) return rc;
-    free_compiled(net->compiled);
-    free_compiled(net->compiled_perm);
-    net->compiled = c;
-    net->compiled_perm = nullptr;
-    net->layers_folded = layers;
+    c->layers_folded = layers;
+    net->variants.insert(net->variants.begin(), c);
+    if (net->variants.size() > CLR_NET_VARIANTS) { free_compiled(net->variants.back()); net->variants.pop_back(); }
     *outc = c;
     return 0;
 }
 
 // The same network with the neurons of every interior layer reordered (rows of W_l and b_l, columns of W_{l+1}):
 // an equivalent parametrisation; `order[l][i]` = original index of the neuron placed at position i of layer l.
-int compile_net_reordered(clr_ctx* ctx, clr_net* net, int n_in, const std::vector<std::vector<int>>& order, Compiled** outc) {
-    std::vector<unsigned char> key = net->compiled->key;
+int compile_net_reordered(clr_ctx* ctx, Compiled* base, int n_in, const std::vector<std::vector<int>>& order, Compiled** outc) {
+    std::vector<unsigned char> key = base->key;
     for (const auto& o : order) {
         const unsigned char* p = (const unsigned char*)o.data();
         key.insert(key.end(), p, p + sizeof(int) * o.size());
         key.push_back(0xFF);
     }
-    if (net->compiled_perm && net->compiled_perm->key == key) { *outc = net->compiled_perm; return 0; }
-    std::vector<HostLayer> layers = net->layers_folded;
+    if (base->perm && base->perm->key == key) { *outc = base->perm; return 0; }
+    std::vector<HostLayer> layers = base->layers_folded;
     for (size_t l = 0; l + 1 < layers.size(); l++) {
         const std::vector<int>& o = order[l];
         if (o.empty()) continue;
@@ -440,8 +477,8 @@ int compile_net_reordered(clr_ctx* ctx, clr_net* net, int n_in, const std::vecto
     Compiled* c = nullptr;
     int rc = compile_layers(ctx, layers, n_in, key, &c);
     if (rc) return rc;
-    free_compiled(net->compiled_perm);
-    net->compiled_perm = c;
+    free_compiled(base->perm);
+    base->perm = c;
     *outc = c;
     return 0;
 }
@@ -481,7 +518,7 @@ size_t dz_geom(const DevNet& D, bool stats, size_t smem_total, int ncol_need, De
 }
 
 int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int grid, int threads, size_t smem,
-                 const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
+                 const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp, bool wide = false) {
     cudaError_t e;
     const int ksreg = c->ksreg;
     const DevNet* net = c->dev;
@@ -491,11 +528,12 @@ int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int g
         full = full || d.act == CLR_ACT_SIGMOID || d.act == CLR_ACT_TANH || d.ksteps > ksreg;
     }
     full = full || !c->inplace;                 // two-buffer products (a layer wider than 128 neurons)
+    wide = wide && sp.wide && (global || !full);   // the instantiations that exist (deepz_ks.inc)
     switch (ksreg) {   // one translation unit per KSREG (deepz_ks*.cu), so that the instantiations compile in parallel
-        case 8: e = launch_deepz_ks8(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        case 16: e = launch_deepz_ks16(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        case 25: e = launch_deepz_ks25(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        default: e = launch_deepz_ks32(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 8: e = launch_deepz_ks8(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 16: e = launch_deepz_ks16(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 25: e = launch_deepz_ks25(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        default: e = launch_deepz_ks32(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
     }
     if (e != cudaSuccess) return fail(ctx, CLR_ERR_CUDA, "DeepZ kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
@@ -509,13 +547,15 @@ int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int g
 // that count (an equivalent reparametrisation of the network: rows of W_l, b_l and columns of W_{l+1}), which moves
 // the dead rows to the end where deepz_kernel skips their k-steps (S.kAct).  Results change only by the summation
 // order inside the next product (~1e-16 relative).
-int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& in_full, long double total_cells, int n_in,
-                     Compiled** outc) {
+int reorder_for_grid(clr_ctx* ctx, Compiled* c, const DeepzInput& in_full, long double total_cells, int n_in,
+                     const std::vector<unsigned char>& split_key, Compiled** outc) {
     *outc = c;
     const DevNet& D = c->host;
     bool any = false;
     for (int l = 0; l + 1 < D.L; l++) any = any || (D.layer[l].act == CLR_ACT_RELU && D.layer[l].m >= 16);
     if (!any) return 0;
+    // the same split as last time (partition and tables): the order is known, no pilot launch, no synchronisation
+    if (!split_key.empty() && c->pilot_key == split_key) { if (c->perm) *outc = c->perm; return 0; }
     const long long S = (long long)std::min<long double>((long double)CLR_PILOT_CELLS, total_cells);
     std::vector<long long> ids((size_t)S);
     for (long long k = 0; k < S; k++) ids[(size_t)k] = (long long)((total_cells * k) / S);
@@ -527,6 +567,7 @@ int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& 
     CU(cudaMemsetAsync(ctx->d_live, 0, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS, ctx->stream));
     DeepzInput in = in_full;
     in.cell_begin = 0;                    // the list holds ids of the whole split
+    in.cyc_blk = 0; in.cyc_stride = 0;
     in.N = S;
     DeepzOutput out{};
     out.liveCount = ctx->d_live;
@@ -546,7 +587,9 @@ int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& 
     ctx->d_state = saved;
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->h_live, ctx->d_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state2, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    c->pilot_peak_cols = ctx->h_state->max_p_out;
     std::vector<std::vector<int>> order((size_t)D.L);
     bool changed = false;
     for (int l = 0; l + 1 < D.L; l++) {
@@ -559,13 +602,15 @@ int reorder_for_grid(clr_ctx* ctx, clr_net* net, Compiled* c, const DeepzInput& 
         for (int i = 0; i < d.m; i++) changed = changed || o[i] != i;
         order[(size_t)l] = std::move(o);
     }
-    if (!changed) return 0;
-    return compile_net_reordered(ctx, net, n_in, order, outc);
+    c->pilot_key = split_key;
+    if (!changed) { free_compiled(c->perm); c->perm = nullptr; return 0; }
+    return compile_net_reordered(ctx, c, n_in, order, outc);
 }
 
 // Shared driver of clr_deepz_boxgrid / clr_deepz_zonotopes once `in` points at device inputs.
+#define CLR_WIDE_COLS 96   // main pass: cells of this many columns (pilot / input) take the several-threads-per-neuron relaxation
 int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max, double* out_lo, double* out_hi,
-              double* hull_lo, double* hull_hi, clr_stats* stats, int keep_cap, int flags) {
+              double* hull_lo, double* hull_hi, clr_stats* stats, int keep_cap, int flags, int peak_cols_hint = 0) {
     const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
     const bool want_stats = stats != nullptr && !(flags & CLR_FLAG_NO_STATS);
     const DevNet& D = c->host;
@@ -672,6 +717,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         const DevLayer& lt = D.layer[D.L - 1];
         sp.fuse_tail = D.L >= 2 && lt.act == CLR_ACT_ID && lt.m <= 4 && lt.n <= 4 && !lt.remove_zero && keep_cap == 0;
     }
+    sp.wide = sp.grow_cols == 0;      // networks whose cell widths are data dependent (ReLU); sigmoid / tanh tiles are sized exactly
     sp.retry_list = ctx->d_retry;
     sp.big_list = ctx->d_big;
     sp.workspace = nullptr;
@@ -680,7 +726,9 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     sp.pass = 0;
     ctx->pass_ms[0] = ctx->pass_ms[1] = ctx->pass_ms[2] = 0.f;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
+    bool wide_main = std::max(peak_cols_hint, 1 + p0max) >= CLR_WIDE_COLS;
+    if (const char* force = getenv("CLR_B200_WIDE")) wide_main = force[0] == '1';     // A/B switch of profiles/ab_bench.py
+    if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp, wide_main))) return rc;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
     bool fast_done = false;
@@ -694,7 +742,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         fast_done = ctx->h_state->n_retry == 0 && ctx->h_state->n_big == 0;
     }
     if (!fast || ctx->h_state->n_retry > 0) {
-        if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
+        if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp, getenv("CLR_B200_WIDE") ? wide_main : true))) return rc;   // cells that overflowed a tile: wide
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         // how many cells did not fit in shared memory at all?
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -711,7 +759,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         DeepzSched sg = sp;
         sg.pass = 2;
         const int stageW = std::max(clr_pad4(D.max_rows), 2 * D.n_in);
-        sg.cap = (wc + 8) * D.max_pitch * (c->inplace ? 1 : 2) + stageW + 64;
+        sg.cap = (wc + 8) * D.max_pitch * (c->inplace ? 1 : 2) + stageW + 64 + 4 * clr_pad4(D.max_rows);   // + the wide relaxation's scratch (DZ_WCH per row)
         int gridg = (int)std::min<unsigned long long>((unsigned long long)ctx->sms, ctx->h_state->n_big);
         size_t need = sizeof(double) * (size_t)gridg * sg.cap;
         if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, need))) return rc;
@@ -719,7 +767,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         const size_t metag = dz_geom(D, kstats, smem_total, wc + 8 + 40, sg);     // one wide cell per tile
         if (metag > smem_total) return fail(ctx, CLR_ERR_CAPACITY, "a cell with %d columns exceeds the tile metadata", wc);
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        if ((rc = launch_deepz(ctx, true, kstats, c, gridg, threads, metag, in, out, sg))) return rc;
+        if ((rc = launch_deepz(ctx, true, kstats, c, gridg, threads, metag, in, out, sg, getenv("CLR_B200_WIDE") ? wide_main : true))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -820,6 +868,7 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_chk, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_bounce, CLR_BOUNCE_BYTES);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_bounce, CLR_BOUNCE_BYTES);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state2, sizeof(DevCallState));
@@ -851,6 +900,7 @@ void clr_destroy(clr_ctx* ctx) {
     cudaFree(ctx->d_keepC);
     cudaFree(ctx->d_keepG);
     cudaFree(ctx->d_err);
+    cudaFree(ctx->d_chk);
     cudaFreeHost(ctx->h_bounce);
     cudaFree(ctx->d_bounce);
     cudaFree(ctx->d_state2);
@@ -900,6 +950,15 @@ int32_t clr_memcpy_d2h(clr_ctx* ctx, void* dst, const void* src, int64_t bytes) 
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+int32_t clr_last_device_error(clr_ctx* ctx, int32_t* code) {
+    if (!ctx || !code) return CLR_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *code = err;
+    return 0;
+}
 int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells) {
     if (!ctx || cells < 0 || cells > CLR_TILE_CELLS_MAX) return fail(ctx, CLR_ERR_ARG, "tile cells must be in 0..%d", CLR_TILE_CELLS_MAX);
     ctx->tile_cells = cells;
@@ -924,6 +983,34 @@ int32_t clr_last_pass_info(clr_ctx* ctx, double* pass_ms, int64_t* retried, int6
     return 0;
 }
 
+int32_t clr_measure_fp64_peak(clr_ctx* ctx, double ms, double* tflops) {
+    if (!ctx || !tflops) return CLR_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    const int grid = ctx->sms * 2, threads = 256;
+    int rc = ensure(ctx, &ctx->d_io[0], &ctx->io_bytes[0], sizeof(double) * (size_t)grid * threads);
+    if (rc) return rc;
+    cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1];
+    auto run = [&](int iters, float* t) -> cudaError_t {
+        cudaError_t e = cudaEventRecord(e0, ctx->stream);
+        if (e != cudaSuccess) return e;
+        fp64_peak_kernel<<<grid, threads, 0, ctx->stream>>>((double*)ctx->d_io[0], iters, 1.0000001, 0.9999999);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(e1, ctx->stream)) != cudaSuccess) return e;
+        if ((e = cudaEventSynchronize(e1)) != cudaSuccess) return e;
+        return cudaEventElapsedTime(t, e0, e1);
+    };
+    float t = 0.f;
+    CU(run(2000, &t));                                   // warm-up, and the rate for sizing the timed launch
+    CU(run(2000, &t));
+    const double per_iter = (double)t / 2000.0;
+    const int iters = (int)std::min(5.0e7, std::max(2000.0, (ms > 0 ? ms : 20.0) / std::max(per_iter, 1e-9)));
+    CU(run(iters, &t));
+    ctx->launches += 3;
+    const double flop = 512.0 * 8.0 * (double)iters * (double)grid * (threads / 32);
+    *tflops = flop / ((double)t * 1e-3) / 1e12;
+    return 0;
+}
+
 // DZ_TIMING builds only: cycles per phase of the last DeepZ call, summed over CTAs (not part of the public header)
 int32_t clr_debug_timers(clr_ctx* ctx, unsigned long long* out8) {
     if (!ctx || !out8) return CLR_ERR_ARG;
@@ -945,6 +1032,7 @@ int32_t clr_net_upload(clr_ctx* ctx, int32_t n_layers, const int32_t* dims, cons
     }
     clr_net* net = new clr_net();
     net->ctx = ctx;
+    net->device = ctx->device;
     net->L = n_layers;
     net->dims.assign(dims, dims + n_layers + 1);
     net->act.assign(act, act + n_layers);
@@ -958,9 +1046,8 @@ int32_t clr_net_upload(clr_ctx* ctx, int32_t n_layers, const int32_t* dims, cons
 
 void clr_net_free(clr_net* net) {
     if (!net) return;
-    if (net->ctx) cudaSetDevice(net->ctx->device);
-    free_compiled(net->compiled);
-    free_compiled(net->compiled_perm);
+    cudaSetDevice(net->device);
+    for (Compiled* c : net->variants) free_compiled(c);
     delete net;
 }
 
@@ -969,6 +1056,14 @@ int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net_c, int32_t n, const i
                           int64_t cell_count, const clr_prepost* pp, double* out_lo, double* out_hi,
                           double* hull_lo, double* hull_hi, clr_stats* stats, int32_t keep_cap,
                           int32_t flags) {
+    return clr_deepz_boxgrid_cyclic(ctx, net_c, n, partition, centers, radii, cell_begin, cell_count, 0, 0, pp, out_lo, out_hi,
+                                    hull_lo, hull_hi, stats, keep_cap, flags);
+}
+
+int32_t clr_deepz_boxgrid_cyclic(clr_ctx* ctx, const clr_net* net_c, int32_t n, const int32_t* partition,
+                                 const double* centers, const double* radii, int64_t cell_begin, int64_t cell_count,
+                                 int64_t block, int64_t stride, const clr_prepost* pp, double* out_lo, double* out_hi,
+                                 double* hull_lo, double* hull_hi, clr_stats* stats, int32_t keep_cap, int32_t flags) {
     if (!ctx) return CLR_ERR_ARG;
     clr_net* net = const_cast<clr_net*>(net_c);
     if (!net || !partition || !centers || !radii) return fail(ctx, CLR_ERR_ARG, "clr_deepz_boxgrid: NULL argument");
@@ -984,8 +1079,13 @@ int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net_c, int32_t n, const i
         tab += partition[d];
         total *= partition[d];
     }
-    if (cell_begin < 0 || cell_count < 0 || (long double)cell_begin + (long double)cell_count > total)
-        return fail(ctx, CLR_ERR_ARG, "cell range [%lld, %lld) outside the split", (long long)cell_begin, (long long)(cell_begin + cell_count));
+    if (block < 0 || stride < 0 || (block > 0 && stride < block))
+        return fail(ctx, CLR_ERR_ARG, "block-cyclic ids need 0 < block <= stride (got block %lld, stride %lld)", (long long)block, (long long)stride);
+    long double last = (long double)cell_begin + (long double)cell_count;        // one past the last id of the call
+    if (block > 0 && cell_count > 0)
+        last = (long double)cell_begin + (long double)((cell_count - 1) / block) * (long double)stride + (long double)((cell_count - 1) % block) + 1;
+    if (cell_begin < 0 || cell_count < 0 || last > total)
+        return fail(ctx, CLR_ERR_ARG, "cell range [%lld, %lld) outside the split", (long long)cell_begin, (long long)last);
     Compiled* c = nullptr;
     int rc = compile_net(ctx, net, pp, n, &c);
     if (rc) return rc;
@@ -995,7 +1095,9 @@ int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net_c, int32_t n, const i
     if ((rc = stage_in(ctx, 0, centers, sizeof(double) * tab, dev_io, &dc))) return rc;
     if ((rc = stage_in(ctx, 1, radii, sizeof(double) * tab, dev_io, &dr))) return rc;
     in.kind = 0; in.n = n; in.N = cell_count; in.cell_begin = cell_begin;
+    in.cyc_blk = block; in.cyc_stride = stride;
     in.centers = (const double*)dc; in.radii = (const double*)dr;
+    int peak_hint = 0;
     if (ctx->reorder && keep_cap == 0 && cell_count >= CLR_REORDER_MIN_CELLS) {
         if (cell_count > ctx->list_cap) {       // the pilot borrows the large-cell list of the real run
             if (ctx->d_retry) CU(cudaFree(ctx->d_retry));
@@ -1005,9 +1107,18 @@ int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net_c, int32_t n, const i
             CU(cudaMalloc((void**)&ctx->d_big, sizeof(long long) * (size_t)cell_count));
             ctx->list_cap = cell_count;
         }
-        if ((rc = reorder_for_grid(ctx, net, c, in, total, n, &c))) return rc;
+        // key of the split: partition + tables (host tables by value; device-resident tables by address -- a stale order is
+        // still a valid order, it only skips fewer k-steps)
+        std::vector<unsigned char> sk;
+        auto put = [&](const void* p, size_t nb) { const unsigned char* q = (const unsigned char*)p; sk.insert(sk.end(), q, q + nb); };
+        put(partition, sizeof(int32_t) * n);
+        if (dev_io) { put(&centers, sizeof(centers)); put(&radii, sizeof(radii)); }
+        else { put(centers, sizeof(double) * tab); put(radii, sizeof(double) * tab); }
+        Compiled* base = c;
+        if ((rc = reorder_for_grid(ctx, c, in, total, n, sk, &c))) return rc;
+        peak_hint = base->pilot_peak_cols;
     }
-    return run_deepz(ctx, net, c, in, n, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags);
+    return run_deepz(ctx, net, c, in, n, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags, peak_hint);
 }
 
 int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net_c, int32_t n, int64_t N, const double* C,
@@ -1030,12 +1141,16 @@ int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net_c, int32_t n, int64
     if (N > 0) {
         const void *dC, *dO, *dG;
         if (dev_io) {
-            CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
-            max_cols_kernel<<<std::min<long long>(1024, (N + 255) / 256), 256, 0, ctx->stream>>>((const long long*)col_off, N, ctx->d_err);
+            int mm[2] = {0, 0x7fffffff};
+            CU(cudaMemcpyAsync(ctx->d_chk, mm, sizeof(mm), cudaMemcpyHostToDevice, ctx->stream));
+            max_cols_kernel<<<std::min<long long>(1024, (N + 255) / 256), 256, 0, ctx->stream>>>((const long long*)col_off, nullptr, N, ctx->d_chk);
             CU(cudaGetLastError());
             ctx->launches++;
-            CU(cudaMemcpyAsync(&p0max, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(mm, ctx->d_chk, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
+            if (mm[1] < 0) return fail(ctx, CLR_ERR_ARG, "col_off must start at 0 and be non-decreasing");
+            if (mm[0] > CLR_NCOL_MAX - 8) return fail(ctx, CLR_ERR_ARG, "a cell has %d generators; at most %d supported", mm[0], CLR_NCOL_MAX - 8);
+            p0max = mm[0];
             dC = C; dO = col_off; dG = G;
         } else {
             if (col_off[0] != 0) return fail(ctx, CLR_ERR_ARG, "col_off[0] must be 0");
@@ -1073,9 +1188,19 @@ int32_t clr_deepz_zonotopes_padded(clr_ctx* ctx, const clr_net* net_c, int32_t n
     ctx->bounce_open = !dev_io; ctx->bounce_used = ctx->bounce_flushed = 0;
     if (N > 0) {
         const void *dC, *dG, *dN;
-        if (!dev_io)
+        if (!dev_io) {
             for (int64_t i = 0; i < N; i++)
                 if (ncols[i] < 0 || ncols[i] > cap) return fail(ctx, CLR_ERR_ARG, "ncols[%lld] = %d outside 0..cap = %d", (long long)i, ncols[i], cap);
+        } else {
+            int mm[2] = {0, 0x7fffffff};
+            CU(cudaMemcpyAsync(ctx->d_chk, mm, sizeof(mm), cudaMemcpyHostToDevice, ctx->stream));
+            max_cols_kernel<<<std::min<long long>(1024, (N + 255) / 256), 256, 0, ctx->stream>>>(nullptr, (const int*)ncols, N, ctx->d_chk);
+            CU(cudaGetLastError());
+            ctx->launches++;
+            CU(cudaMemcpyAsync(mm, ctx->d_chk, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (mm[1] < 0 || mm[0] > cap) return fail(ctx, CLR_ERR_ARG, "ncols outside 0..cap = %d (min %d, max %d)", cap, mm[1], mm[0]);
+        }
         if ((rc = stage_in(ctx, 0, C, sizeof(double) * (size_t)n * N, dev_io, &dC))) return rc;
         if ((rc = stage_in(ctx, 1, ncols, sizeof(int32_t) * (size_t)N, dev_io, &dN))) return rc;
         if ((rc = stage_in(ctx, 2, G, sizeof(double) * (size_t)n * cap * N, dev_io, &dG))) return rc;
@@ -1417,13 +1542,13 @@ int32_t clr_plant_compile(clr_ctx* ctx, int32_t n_state, int32_t n_dist, int32_t
     *out = nullptr;
     if (n_state < 1 || n_state > 32 || n_dist < 0 || n_ctrl < 1 || n_dist + n_ctrl > 32)
         return fail(ctx, CLR_ERR_DIM, "plant dimensions out of range (1..32 states, at most 32 disturbances + controls)");
-    char defs[640];
+    char defs[768];
     snprintf(defs, sizeof(defs),
              "#define CLR_DEV_MAX_LAYERS %d\n"
              "enum { CLR_ACT_ID = 0, CLR_ACT_RELU = 1, CLR_ACT_SIGMOID = 2, CLR_ACT_TANH = 3 };\n"
              "enum { CLR_ALG_TSIT5 = 0, CLR_ALG_RK4 = 1 };\n"
              "enum { CLR_PLANT_UNICYCLE = 1, CLR_PLANT_TORA = 2, CLR_PLANT_ACC = 3, CLR_PLANT_INVPEND = 4 };\n"
-             "#define CLR_ERR_CAPACITY (-2)\n"
+             "#define CLR_ERR_CAPACITY (-2)\n#define CLR_ERR_UNSTABLE (-7)\n"
              "#define CLR_USER_NS %d\n#define CLR_USER_ND %d\n#define CLR_USER_NC %d\n"
              "__device__ void clr_user_rhs(const double* x, const double* q, double* dx);\n",
              CLR_DEV_MAX_LAYERS, n_state, n_dist, n_ctrl);
@@ -1568,6 +1693,9 @@ static int32_t rollout_impl(clr_ctx* ctx, const clr_net* net_c, const clr_prepos
         int err = 0;
         CU(cudaMemcpyAsync(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        if (err == CLR_ERR_UNSTABLE)
+            return fail(ctx, err, "an integration gave up (non-finite error estimate or step, step below eps(t), or more than 1e5 "
+                        "iterations in one control period): OrdinaryDiffEq's retcodes Unstable / DtLessThanMin / MaxIters");
         if (err) return fail(ctx, err, "step log overflow: a period took more than log_cap - 1 = %d accepted steps", log_cap - 1);
     }
     return 0;
@@ -1596,3 +1724,5 @@ int32_t clr_rollout_plant(clr_ctx* ctx, const clr_net* net, const clr_prepost* p
 }
 
 }  // extern "C"
+
+#include "multi.inc"

@@ -213,6 +213,32 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
     }
 }
 
+// The bounds of a neuron are c -/+ rad with rad = sum_j |g_j|.  The sum is DEFINED chunk-wise: the generators in chunks of
+// dz_chunk(p) consecutive columns (a function of the cell's generator count alone), each chunk summed sequentially in
+// ascending order, the chunk sums added up in ascending order.  Cells of up to 128 generators -- every cell of the
+// reference's own problem sizes -- have chunks of 32; there are never more than DZ_WCH chunks.  Wide cells (hundreds of
+// generators when most neurons are unstable) can then be summed by several threads per neuron without the result depending
+// on how the work was dealt (tile size, shard, pass, kernel instantiation).
+#define DZ_WCH 4           // chunks per row at most: scratch of the wide relaxation, DZ_WCH doubles per (cell, row)
+#define DZ_WIDE_MIN 64     // tiles whose widest cell has fewer columns keep one thread per neuron
+__device__ __forceinline__ int dz_chunk(int p) {      // 32, 64, 128, ... : the smallest such that 4 chunks cover p generators
+    int ch = 32;
+    while (ch * DZ_WCH < p) ch <<= 1;
+    return ch;
+}
+// sum of |y[j P]| for j in [j0, j1), ascending, 8 loads in flight
+__device__ __forceinline__ double dz_abs_sum(const double* y, int P, int j0, int j1) {
+    double r = 0.0;
+    for (int j = j0; j < j1; j += 8) {
+        double t[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) t[q] = j + q < j1 ? y[(j + q) * P] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) r += fabs(t[q]);       // + 0.0 beyond j1: exact
+    }
+    return r;
+}
+
 __device__ __forceinline__ double dz_sigm(double x) { return 1.0 / (1.0 + exp(-x)); }
 __device__ __forceinline__ double dz_sigm_p(double x) { double ex = exp(x); return ex / ((1.0 + ex) * (1.0 + ex)); }
 __device__ __forceinline__ double dz_tanh_p(double x) { double t = tanh(x); return 1.0 - t * t; }
@@ -281,13 +307,53 @@ __device__ __forceinline__ void dz_mark_dead(unsigned* dead, const int* colOff, 
     __syncthreads();
 }
 
+// The activation rule of one neuron: bounds -> (new centre, slope, new generator); true when a generator is appended.
+template <bool FULL>
+__device__ __forceinline__ bool dz_rule(int act, double c, double lo, double hi, double& cn, double& la, double& mm) {
+    cn = c; la = 1.0; mm = 0.0;
+    if (act == CLR_ACT_RELU) {
+        if (dz_leq(lo, 0.0)) {
+            if (dz_leq(hi, 0.0)) { cn = 0.0; la = 0.0; }
+            else {
+                la = hi / (hi - lo);
+                mm = -la * lo / 2;
+                cn = c * la + mm;
+                return true;
+            }
+        }
+    } else if (FULL && (act == CLR_ACT_SIGMOID || act == CLR_ACT_TANH)) {
+        // the transcendental calls side by side, so that their (independent) instruction chains interleave;
+        // the same formulas and values as dz_sigm / dz_sigm_p / dz_tanh_p
+        double ly, uy, dl, du;
+        if (act == CLR_ACT_SIGMOID) {
+            const double eml = exp(-lo), emh = exp(-hi), el = exp(lo), eh = exp(hi);
+            ly = 1.0 / (1.0 + eml); uy = 1.0 / (1.0 + emh);
+            dl = el / ((1.0 + el) * (1.0 + el)); du = eh / ((1.0 + eh) * (1.0 + eh));
+        } else {
+            ly = tanh(lo); uy = tanh(hi);
+            dl = 1.0 - ly * ly; du = 1.0 - uy * uy;
+        }
+        if (dz_approx(lo, hi)) { cn = uy; la = 0.0; }
+        else {
+            la = dl < du ? dl : du;
+            double mu1 = (uy + ly - la * (hi + lo)) / 2;
+            mm = (uy - ly - la * (hi - lo)) / 2;
+            cn = c * la + mu1;
+            return true;
+        }
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------------------------------------
 // The persistent tile kernel.
 // ---------------------------------------------------------------------------------------------
 // FULL = false: the lean instantiation for ReLU / Id networks whose layers all keep their W fragments in registers -- no
 // sigmoid / tanh code and no streamed (K > 4 KSREG) products.  The kernel is sensitive to its own size (registers live
 // across the relaxation, instruction fetch): the lean variant is 5 % faster on the same work.
-template <int KSREG, bool GLOBAL, bool STATS, bool FULL>
+// WIDE = true: tiles of few, wide cells relax with several threads per neuron (chosen by the host when the pilot run saw wide cells,
+// and for the retry / global-store passes); same results as WIDE = false bit for bit (dz_chunk).
+template <int KSREG, bool GLOBAL, bool STATS, bool FULL, bool WIDE>
 __global__ void __launch_bounds__(DZ_THREADS, 1)
 deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, DevCallState* st, DeepzSched sp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -381,7 +447,13 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         if (!S.more) break;
         int nCells = S.nCells;
         // store geometry of this tile: [columns ... | staging (nCells x stageW)]
-        const int stageOff = sp.cap - nCells * stageW;
+        // tiles of few, wide cells reserve DZ_WCH doubles per (cell, row) behind the staging area: the chunk sums of the
+        // relaxation with several threads per neuron (decided per tile, before any cell is deferred)
+        const int rowsMaxP = clr_pad4(net->max_rows);
+        const bool wideOk = WIDE && nCells * 2 <= NT / rowsMaxP;
+        const int scratchW = wideOk ? nCells * DZ_WCH * rowsMaxP : 0;
+        double* const wscr = store + (sp.cap - scratchW);
+        const int stageOff = sp.cap - scratchW - nCells * stageW;
         double* stage = store + stageOff;
         const int region = inplace ? stageOff : stageOff / 2;
         const int capCols = min(region / P, sp.ncol_max);
@@ -404,7 +476,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         if (in.kind == 0) {
             for (int it = tid; it < nCells * n; it += NT) {
                 const int ci = it / n, d = it - ci * n;
-                const unsigned long long g = (unsigned long long)(in.cell_begin + S.cellId[ci]);
+                const long long li = S.cellId[ci];
+                const unsigned long long g = (unsigned long long)(in.cyc_blk > 0 ? in.cell_begin + (li / in.cyc_blk) * in.cyc_stride + li % in.cyc_blk
+                                                                                   : in.cell_begin + li);
                 const unsigned long long sd = (unsigned long long)in.stride[d];   // can exceed 2^32 even when g does not
                 int k;
                 if (sd > g) k = 0;
@@ -635,83 +709,45 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             // ---- relaxation: bounds, lambda, mu, rows scaled in place; thread = (cell slot, row) ------------------------
             if (relax) {
                 unsigned rowLive = 0;                     // 1 + the highest row this thread left non-zero
-                // the activation rule of one neuron: bounds -> (new centre, slope, new generator)
-                auto rule = [&](double c, double lo, double hi, double& cn, double& la, double& mm) -> bool {
-                    cn = c; la = 1.0; mm = 0.0;
-                    if (act == CLR_ACT_RELU) {
-                        if (dz_leq(lo, 0.0)) {
-                            if (dz_leq(hi, 0.0)) { cn = 0.0; la = 0.0; }
-                            else {
-                                la = hi / (hi - lo);
-                                mm = -la * lo / 2;
-                                cn = c * la + mm;
-                                return true;
-                            }
-                        }
-                    } else if (FULL && (act == CLR_ACT_SIGMOID || act == CLR_ACT_TANH)) {
-                        // the transcendental calls side by side, so that their (independent) instruction chains interleave;
-                        // the same formulas and values as dz_sigm / dz_sigm_p / dz_tanh_p
-                        double ly, uy, dl, du;
-                        if (act == CLR_ACT_SIGMOID) {
-                            const double eml = exp(-lo), emh = exp(-hi), el = exp(lo), eh = exp(hi);
-                            ly = 1.0 / (1.0 + eml); uy = 1.0 / (1.0 + emh);
-                            dl = el / ((1.0 + el) * (1.0 + el)); du = eh / ((1.0 + eh) * (1.0 + eh));
-                        } else {
-                            ly = tanh(lo); uy = tanh(hi);
-                            dl = 1.0 - ly * ly; du = 1.0 - uy * uy;
-                        }
-                        if (dz_approx(lo, hi)) { cn = uy; la = 0.0; }
-                        else {
-                            la = dl < du ? dl : du;
-                            double mu1 = (uy + ly - la * (hi + lo)) / 2;
-                            mm = (uy - ly - la * (hi - lo)) / 2;
-                            cn = c * la + mu1;
-                            return true;
-                        }
-                    }
-                    return false;
-                };
-                {
-                    const int G = NT / rowsP;                 // cell slots processed side by side
-                    const int slot = tid / rowsP, r = tid - slot * rowsP;
+                const int G = NT / rowsP;                 // cell slots processed side by side
+                const int slot = tid / rowsP, r = tid - slot * rowsP;
+                // threads per neuron: 1, or -- few wide cells -- several, each summing whole chunks of the row
+                int tpr = 1;
+                if (WIDE && wideOk && nCells * 2 <= G) {
+                    int wmax = 0;
+                    for (int ci = 0; ci < nCells; ci++) wmax = max(wmax, (int)wCur[ci] + (int)S.uPend[flip][ci]);
+                    if (wmax >= DZ_WIDE_MIN) tpr = min(DZ_WCH, G / nCells);
+                }
+                if (!WIDE || tpr == 1) {
                     if (slot < G && r < m) {
                         const double bias = __ldg(Ly.bias + r);
                         for (int ci = slot; ci < nCells; ci += G) {
                             const int w = wCur[ci] + S.uPend[flip][ci];
                             const int cb = colOff[ci];
                             double* y = cur + cb * P + r;
-                            // the row is read in chunks of 8 generators, all loads of a chunk in flight before the (sequential,
-                            // reference-ordered) sums; the first chunk stays in registers for the scaling below
+                            const int chm = dz_chunk(w - 1) - 1;      // chunk boundaries in front of the generators 1 + k * chunk
+                            // the row is read in groups of 8 generators, all loads of a group in flight before the (sequential)
+                            // sums; the first group stays in registers for the scaling below
                             double v[8];
 #pragma unroll
                             for (int q = 0; q < 8; q++) v[q] = q + 1 < w ? y[(q + 1) * P] : 0.0;
-                            double c = y[0] + bias, lo, hi, rad = 0.0;
-                            if (collapse) {
+                            const double c = y[0] + bias;
+                            double rad = 0.0, part = 0.0;
 #pragma unroll
-                                for (int q = 0; q < 8; q++) rad += fabs(v[q]);       // + 0.0 beyond w: exact
-                                for (int j0 = 9; j0 < w; j0 += 8) {
-                                    double t[8];
+                            for (int q = 0; q < 8; q++) part += fabs(v[q]);       // + 0.0 beyond w: exact
+                            for (int j0 = 9; j0 < w; j0 += 8) {
+                                if (((j0 - 1) & chm) == 0) { rad += part; part = 0.0; }
+                                double t[8];
 #pragma unroll
-                                    for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
+                                for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
 #pragma unroll
-                                    for (int q = 0; q < 8; q++) rad += fabs(t[q]);
-                                }
-                                lo = c - rad; hi = c + rad;
-                            } else {
-                                lo = c; hi = c;
-#pragma unroll
-                                for (int q = 0; q < 8; q++) { const double av = fabs(v[q]); lo -= av; hi += av; }
-                                for (int j0 = 9; j0 < w; j0 += 8) {
-                                    double t[8];
-#pragma unroll
-                                    for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
-#pragma unroll
-                                    for (int q = 0; q < 8; q++) { const double av = fabs(t[q]); lo -= av; hi += av; }
-                                }
+                                for (int q = 0; q < 8; q++) part += fabs(t[q]);
                             }
+                            rad += part;
+                            const double lo = c - rad, hi = c + rad;
                             if (STATS && act == CLR_ACT_RELU && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
                             double cn, la, mm;
-                            const bool unst = rule(c, lo, hi, cn, la, mm);
+                            const bool unst = dz_rule<FULL>(act, c, lo, hi, cn, la, mm);
                             if (cn != 0.0 || la != 0.0) {
                                 rowLive = r + 1;
                                 if (out.liveCount) atomicAdd(&out.liveCount[l * CLR_MAX_ROWS + r], 1);
@@ -733,6 +769,60 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                             if (unst) {
                                 stage[ci * stageW + r] = mm;
                                 atomicOr(&fresh[ci * mS + (r >> 5)], 1u << (r & 31));
+                            }
+                        }
+                    }
+                } else {
+                    // ---- several threads per neuron: thread (cell, part, row) sums the chunks k = part, part + tpr, ... of its row,
+                    // the part-0 thread adds the chunk sums up in ascending order and applies the rule, all of them scale ----
+                    const int ci = slot / tpr, part = slot - ci * tpr;
+                    const bool on = slot < nCells * tpr && r < m;
+                    int w = 0, CH = 32, nCh = 1;
+                    double* y = cur;
+                    double* const myScr = wscr + (ci * DZ_WCH) * rowsMaxP + r;      // [chunk] stride rowsMaxP; slot 0: the slope
+                    if (on) {
+                        w = wCur[ci] + S.uPend[flip][ci];
+                        y = cur + colOff[ci] * P + r;
+                        CH = dz_chunk(w - 1); nCh = max(1, (w - 1 + CH - 1) / CH);
+                        for (int k = part; k < nCh; k += tpr) myScr[k * rowsMaxP] = dz_abs_sum(y, P, 1 + k * CH, min(w, 1 + (k + 1) * CH));
+                    }
+                    __syncthreads();
+                    if (on && part == 0) {
+                        const double c = y[0] + __ldg(Ly.bias + r);
+                        double rad = 0.0;
+                        for (int k = 0; k < nCh; k++) rad += myScr[k * rowsMaxP];
+                        const double lo = c - rad, hi = c + rad;
+                        if (STATS && act == CLR_ACT_RELU && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
+                        double cn, la, mm;
+                        const bool unst = dz_rule<FULL>(act, c, lo, hi, cn, la, mm);
+                        if (cn != 0.0 || la != 0.0) {
+                            rowLive = r + 1;
+                            if (out.liveCount) atomicAdd(&out.liveCount[l * CLR_MAX_ROWS + r], 1);
+                        }
+                        y[0] = cn;
+                        if (collapse) y[P] = la * rad;
+                        myScr[0] = la;
+                        if (unst) {
+                            stage[ci * stageW + r] = mm;
+                            atomicOr(&fresh[ci * mS + (r >> 5)], 1u << (r & 31));
+                        }
+                    }
+                    __syncthreads();
+                    if (on && !collapse) {
+                        const double la = myScr[0];
+                        if (la != 1.0) {
+                            for (int k = part; k < nCh; k += tpr) {
+                                const int j0 = 1 + k * CH, j1 = min(w, 1 + (k + 1) * CH);
+                                if (la == 0.0) { for (int j = j0; j < j1; j++) y[j * P] = 0.0; }
+                                else {
+                                    for (int j = j0; j < j1; j += 8) {
+                                        double t[8];
+#pragma unroll
+                                        for (int q = 0; q < 8; q++) t[q] = j + q < j1 ? y[(j + q) * P] : 0.0;
+#pragma unroll
+                                        for (int q = 0; q < 8; q++) if (j + q < j1) y[(j + q) * P] = t[q] * la;
+                                    }
+                                }
                             }
                         }
                     }
@@ -1003,6 +1093,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
         }
         DZ_T(5);
+        if (out.liveCount && tid == 0) atomicMax(&st->max_p_out, (int)S.peakCols);      // pilot runs: columns per cell at the widest layer
         // ---- adapt the tile size to the growth just seen ---------------------------------------------------------------
         if (tid == 0) {
             if (sp.tile_cells <= 0 && sp.pass != 2) {
@@ -1010,6 +1101,8 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 // columns and staging both scale with the number of cells
                 const float perCell = S.peakNeed * margin * (float)P * (inplace ? 1.f : 2.f) + (float)stageW;
                 int T = (int)((float)(sp.cap - 16 * P) / perCell);
+                if (sp.wide && T * 2 <= NT / clr_pad4(net->max_rows))       // such a tile also carries the wide relaxation's scratch
+                    T = (int)((float)(sp.cap - 16 * P) / (perCell + (float)(DZ_WCH * clr_pad4(net->max_rows))));
                 if (sp.grow_cols > 0 && sp.pass == 0) {
                     // sigmoid / tanh layers: the growth of a cell is known, not estimated -- the largest tile whose columns,
                     // 8 columns of slack and staging fit exactly (wide cells: one more cell per tile is a large step)

@@ -8,6 +8,8 @@ struct DeepzInput {
     int n;                    // rows of the input sets
     long long N;              // cells of this call
     long long cell_begin;     // box grid: id of the first cell in product order
+    long long cyc_blk;        // > 0: block-cyclic ids -- local cell i is cell_begin + (i / cyc_blk) * cyc_stride + i % cyc_blk
+    long long cyc_stride;
     int part[64];
     int base[64];
     long long stride[64];     // product of part[0..d-1]
@@ -46,6 +48,7 @@ struct DeepzSched {
     int ncol_max;             // columns a tile may hold (<= CLR_NCOL_MAX); the position table has ncol_max + 32 entries
     int store_off;            // byte offset of the column store in dynamic shared memory
     int fuse_tail;            // 1: the last layer (Id, at most 4 inputs and rows) is applied column by column in the output stage
+    int wide;                 // 1: tiles of few wide cells relax with several threads per neuron (scratch behind the staging area)
     long long* retry_list;
     long long* big_list;
     double* workspace;        // pass 2: gridDim.x * cap doubles

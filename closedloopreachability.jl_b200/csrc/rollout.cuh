@@ -354,7 +354,7 @@ struct RolloutArgs {
     int* log_n;
     double* log_t;
     double* log_u;
-    int* error;            // device flag: CLR_ERR_CAPACITY when a step log overflows
+    int* error;            // device flag: CLR_ERR_CAPACITY when a step log overflows, CLR_ERR_UNSTABLE when an integration gave up
 };
 
 #define TS_A21 0.161
@@ -453,8 +453,11 @@ __device__ __forceinline__ void ro_tsit5(double* x, const double* q, double t0, 
         }
     }
     double qold = 1e-4;
+    // OrdinaryDiffEq stops a solve with retcode MaxIters after maxiters = 1e5 iterations, with Unstable / DtLessThanMin when the
+    // error estimate or the step is not finite or the step underflows; here the period ends and the call reports CLR_ERR_UNSTABLE
     int guard = 0;
-    while (t < t1 && guard++ < 1000000) {
+    while (t < t1) {
+        if (++guard > 100000 || !(fabs(dt) > ro_eps_of(t)) || !isfinite(dt)) { atomicCAS(A.error, 0, (int)CLR_ERR_UNSTABLE); break; }
         if (dt > t1 - t) dt = t1 - t;
 #pragma unroll
         for (int i = 0; i < NS; i++) tmp[i] = x[i] + dt * (TS_A21 * k1[i]);
@@ -488,6 +491,7 @@ __device__ __forceinline__ void ro_tsit5(double* x, const double* q, double t0, 
             se += r * r;
         }
         double EEst = sqrt(se / NE);
+        if (!isfinite(EEst)) { atomicCAS(A.error, 0, (int)CLR_ERR_UNSTABLE); break; }
         double qq, q11 = 0.0;
         if (EEst == 0.0) {
             qq = 1.0 / qmax;

@@ -201,6 +201,18 @@ class Context:
         self._check(self.L.clr_last_pass_info(self.h, ms, C.byref(retried), C.byref(big)))
         return {"pass_ms": list(ms), "retried": retried.value, "big": big.value}
 
+    def last_device_error(self) -> int:
+        """Device-side status word of the last CLR_FLAG_DEVICE_IO call, after synchronising (clr_last_device_error)."""
+        out = C.c_int32()
+        self._check(self.L.clr_last_device_error(self.h, C.byref(out)))
+        return out.value
+
+    def measure_fp64_peak(self, ms: float = 20.0) -> float:
+        """FP64 mma.sync (DMMA) issue peak of this device in TFLOP/s (clr_measure_fp64_peak)."""
+        out = C.c_double()
+        self._check(self.L.clr_measure_fp64_peak(self.h, float(ms), C.byref(out)))
+        return out.value
+
     def upload(self, net: FeedforwardNetwork) -> DeviceNetwork:
         return DeviceNetwork(self, net)
 
@@ -209,7 +221,8 @@ class Context:
 
     # ---- DeepZ ------------------------------------------------------------------------------------
     def deepz_boxgrid(self, dnet: DeviceNetwork, partition, centers, radii, cell_begin=0, cell_count=None,
-                      pre=None, post=None, hull=False, stats=True, keep_cap=0, boxes=True, out_lo=None, out_hi=None):
+                      pre=None, post=None, hull=False, stats=True, keep_cap=0, boxes=True, out_lo=None, out_hi=None,
+                      block=0, stride=0):
         """All cells [cell_begin, cell_begin+cell_count) of a box split through controller_forward.
 
         ``centers`` / ``radii``: per-dimension tables (lists of 1-D arrays; ``radii`` per block).
@@ -232,9 +245,10 @@ class Context:
         hl = np.empty(m) if hull else None
         hh = np.empty(m) if hull else None
         st = _lib.Stats() if stats else None
-        rc = self.L.clr_deepz_boxgrid(self.h, dnet.h, n, _ptr(part), _ptr(cc), _ptr(rr), int(cell_begin),
-                                      int(cell_count), C.byref(pp.s), _ptr(lo), _ptr(hi), _ptr(hl), _ptr(hh),
-                                      C.byref(st) if stats else None, int(keep_cap), 0 if stats else FLAG_NO_STATS)
+        rc = self.L.clr_deepz_boxgrid_cyclic(self.h, dnet.h, n, _ptr(part), _ptr(cc), _ptr(rr), int(cell_begin),
+                                             int(cell_count), int(block), int(stride), C.byref(pp.s), _ptr(lo), _ptr(hi),
+                                             _ptr(hl), _ptr(hh), C.byref(st) if stats else None, int(keep_cap),
+                                             0 if stats else FLAG_NO_STATS)
         self._check(rc)
         out = {"lo": lo, "hi": hi}
         if hull:
@@ -366,11 +380,11 @@ class Context:
 
     # device-resident variant: every data pointer is a device pointer / torch CUDA tensor
     def deepz_boxgrid_dev(self, dnet, n, d_partition_host, d_centers, d_radii, cell_begin, cell_count, pp: PrePostArg,
-                          d_lo, d_hi, d_hull_lo=None, d_hull_hi=None, stats=None, keep_cap=0):
+                          d_lo, d_hi, d_hull_lo=None, d_hull_hi=None, stats=None, keep_cap=0, block=0, stride=0):
         part = np.ascontiguousarray(d_partition_host, dtype=np.int32)
         flags = FLAG_DEVICE_IO | (0 if stats is not None else FLAG_NO_STATS)
-        rc = self.L.clr_deepz_boxgrid(self.h, dnet.h, n, _ptr(part), _ptr(d_centers), _ptr(d_radii),
-                                      int(cell_begin), int(cell_count), C.byref(pp.s), _ptr(d_lo), _ptr(d_hi),
+        rc = self.L.clr_deepz_boxgrid_cyclic(self.h, dnet.h, n, _ptr(part), _ptr(d_centers), _ptr(d_radii),
+                                      int(cell_begin), int(cell_count), int(block), int(stride), C.byref(pp.s), _ptr(d_lo), _ptr(d_hi),
                                       _ptr(d_hull_lo), _ptr(d_hull_hi), C.byref(stats) if stats is not None else None,
                                       int(keep_cap), flags)
         self._check(rc)
@@ -445,3 +459,120 @@ class Context:
                                 float(abstol), float(reltol), int(substeps), int(pow_mode), _ptr(d_X_end), _ptr(d_U),
                                 _ptr(d_naccept), _ptr(d_nreject), 0, None, None, None, FLAG_DEVICE_IO)
         self._check(rc)
+
+
+class MultiContext:
+    """clr_multi: several GPUs of one box behind one handle (one host thread and stream per device inside the library; cells
+    and trajectories sharded by contiguous id range, no exchange step, hulls gathered peer to peer).  Host buffers only."""
+
+    def __init__(self, devices):
+        self.L = _lib.lib()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self.L.clr_create_multi(devs, len(devices), C.byref(h))
+        if rc != 0:
+            _raise(rc, (self.L.clr_last_error(None) or b"").decode())
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.clr_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            _raise(rc, (self.L.clr_multi_last_error(self.h) or b"").decode())
+
+    def __len__(self):
+        return int(self.L.clr_multi_size(self.h))
+
+    def set_reorder(self, on: bool):
+        for i in range(len(self)):
+            self.L.clr_set_reorder(self.L.clr_multi_ctx(self.h, i), 1 if on else 0)
+
+    def launch_count(self):
+        return [int(self.L.clr_launch_count(self.L.clr_multi_ctx(self.h, i))) for i in range(len(self))]
+
+    def upload(self, net: FeedforwardNetwork):
+        return MultiNetwork(self, net)
+
+    def deepz_boxgrid(self, mnet, partition, centers, radii, cell_begin=0, cell_count=None, pre=None, post=None, hull=False,
+                      stats=True, balance=False):
+        part = np.ascontiguousarray(partition, dtype=np.int32)
+        n = len(part)
+        total = int(np.prod(part.astype(object)))
+        if cell_count is None:
+            cell_count = total - cell_begin
+        cc = np.ascontiguousarray(np.concatenate([np.atleast_1d(c) for c in centers]), dtype=np.float64)
+        rr = np.ascontiguousarray(np.concatenate([np.atleast_1d(r) for r in radii]), dtype=np.float64)
+        pp = PrePostArg(pre, post)
+        m = pp.out_dim(mnet.dims[-1])
+        cnt = max(int(cell_count), 0)
+        lo, hi = np.empty((cnt, m)), np.empty((cnt, m))
+        hl = np.empty(m) if hull else None
+        hh = np.empty(m) if hull else None
+        st = _lib.Stats() if stats else None
+        G = len(self)
+        bounds = np.zeros(G + 1, dtype=np.int64)
+        ms = np.zeros(G, dtype=np.float64)
+        rc = self.L.clr_multi_deepz_boxgrid(self.h, mnet.h, n, _ptr(part), _ptr(cc), _ptr(rr), int(cell_begin), int(cell_count),
+                                            C.byref(pp.s), _ptr(lo), _ptr(hi), _ptr(hl), _ptr(hh), C.byref(st) if stats else None,
+                                            {False: 0, True: 1, "cost": 1, "cyclic": 2, 0: 0, 1: 1, 2: 2}[balance], _ptr(bounds), _ptr(ms))
+        self._check(rc)
+        out = {"lo": lo, "hi": hi, "shard_bounds": bounds, "shard_ms": ms}
+        if hull:
+            out.update(hull_lo=hl, hull_hi=hh)
+        if stats:
+            out["stats"] = stats_dict(st, len(mnet.net.layers))
+        return out
+
+    def rollout(self, mnet, plant, x0, Wd, t0, tau, T, iters, alg="Tsit5", abstol=1e-6, reltol=1e-3, substeps=4, pow_mode=1,
+                pre=None, post=None):
+        pid = PLANTS[plant] if isinstance(plant, str) else int(plant)
+        ns, nd, nc = PLANT_DIMS[pid]
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        N = x0.shape[0]
+        Wd = np.ascontiguousarray(Wd, dtype=np.float64).reshape(iters, N, nd) if nd else None
+        pp = PrePostArg(pre, post)
+        X = np.empty((iters, N, ns))
+        U = np.empty((iters, N, nc))
+        na = np.empty((iters, N), dtype=np.int32)
+        nr = np.empty((iters, N), dtype=np.int32)
+        rc = self.L.clr_multi_rollout(self.h, mnet.h, C.byref(pp.s), pid, ns, nd, nc, N, int(iters), _ptr(x0), _ptr(Wd), float(t0),
+                                      float(tau), float(T), 0 if alg == "Tsit5" else 1, float(abstol), float(reltol), int(substeps), int(pow_mode),
+                                      _ptr(X), _ptr(U), _ptr(na), _ptr(nr))
+        self._check(rc)
+        return {"X_end": X, "U": U, "naccept": na, "nreject": nr}
+
+
+class MultiNetwork:
+    """A FeedforwardNetwork replicated on every device of a MultiContext (clr_multi_net)."""
+
+    def __init__(self, mctx: MultiContext, net: FeedforwardNetwork):
+        self.mctx, self.net = mctx, net
+        self.dims = list(net.dims)
+        L = len(net.layers)
+        W = [np.asfortranarray(l.weights, dtype=np.float64) for l in net.layers]
+        b = [np.ascontiguousarray(l.bias, dtype=np.float64) for l in net.layers]
+        dims = (C.c_int32 * (L + 1))(*self.dims)
+        act = (C.c_int32 * L)(*[ACT_IDS[l.activation] for l in net.layers])
+        Wp = (C.c_void_p * L)(*[w.ctypes.data for w in W])
+        bp = (C.c_void_p * L)(*[x.ctypes.data for x in b])
+        h = C.c_void_p()
+        mctx._check(mctx.L.clr_multi_net_upload(mctx.h, L, dims, act, Wp, bp, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.mctx.h:
+                self.mctx.L.clr_multi_net_free(self.h)
+        except Exception:
+            pass
+        self.h = None

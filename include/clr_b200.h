@@ -49,7 +49,8 @@ typedef enum {
     CLR_ERR_DIM = -3,        /* dimension mismatch (Julia side: ArgumentError, src/solve.jl:130-134) */
     CLR_ERR_CUDA = -4,       /* CUDA runtime error or no device */
     CLR_ERR_ALLOC = -5,
-    CLR_ERR_STATE = -6       /* call order (e.g. fetch before a keep run) */
+    CLR_ERR_STATE = -6,      /* call order (e.g. fetch before a keep run) */
+    CLR_ERR_UNSTABLE = -7    /* a rollout integration gave up: OrdinaryDiffEq's retcodes Unstable / DtLessThanMin / MaxIters */
 } clr_status;
 
 /* activations (ControllerFormats names) */
@@ -112,6 +113,9 @@ int32_t clr_device_alloc(clr_ctx* ctx, int64_t bytes, void** out);
 int32_t clr_device_free(clr_ctx* ctx, void* p);
 int32_t clr_memcpy_h2d(clr_ctx* ctx, void* dst, const void* src, int64_t bytes);
 int32_t clr_memcpy_d2h(clr_ctx* ctx, void* dst, const void* src, int64_t bytes);
+/* CLR_FLAG_DEVICE_IO calls return before their kernels have run: the device-side status word of the last rollout / order
+   reduction / zonotope check (0, CLR_ERR_CAPACITY, CLR_ERR_UNSTABLE, CLR_ERR_ARG) after synchronising the stream */
+int32_t clr_last_device_error(clr_ctx* ctx, int32_t* code);
 /* tuning knob of the DeepZ tile scheduler: cells per tile (0 = automatic) */
 int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells);
 /* Neuron reordering of large box-grid calls (default on): a pilot run over 2048 cells of the WHOLE split counts how often
@@ -124,6 +128,10 @@ int32_t clr_set_profiling(clr_ctx* ctx, int32_t on);
 /* device time (ms) of the three passes of the last DeepZ call (needs profiling on), the number of
    cells that were retried alone and the number that went through the global-store pass */
 int32_t clr_last_pass_info(clr_ctx* ctx, double* pass_ms /*3*/, int64_t* retried, int64_t* big);
+/* The roofline denominator of the layer products, measured on THIS device: a register-only loop of independent FP64
+   mma.sync.m8n8k4 (SASS DMMA) chains on every SM for about `ms` milliseconds; *tflops = 512 FLOP per warp instruction /
+   time (CUDA events).  MEASURED_PEAKS.json carries no FP64 figure, so bench.py measures it in the same run. */
+int32_t clr_measure_fp64_peak(clr_ctx* ctx, double ms, double* tflops);
 
 /* ---- networks ------------------------------------------------------------------------------ */
 /* dims has n_layers+1 entries; W[l] is dims[l+1] x dims[l] column-major, b[l] has dims[l+1] entries */
@@ -150,6 +158,14 @@ int32_t clr_deepz_boxgrid(clr_ctx* ctx, const clr_net* net, int32_t n, const int
                           int64_t cell_count, const clr_prepost* pp, double* out_lo, double* out_hi,
                           double* hull_lo, double* hull_hi, clr_stats* stats, int32_t keep_cap,
                           int32_t flags);
+/* Block-cyclic ids (block > 0): local cell i of the call is cell  cell_begin + (i / block) * stride + i % block  of the split;
+   results are in local order.  Device r of G takes cell_begin = first + r * block and stride = G * block: its share is then
+   spread evenly over the whole range, so that shards take the same time without a cost model (sharding is this library's own:
+   the reference's loop is serial, src/solve.jl:153-166).  block = 0: contiguous, = clr_deepz_boxgrid. */
+int32_t clr_deepz_boxgrid_cyclic(clr_ctx* ctx, const clr_net* net, int32_t n, const int32_t* partition,
+                                 const double* centers, const double* radii, int64_t cell_begin, int64_t cell_count,
+                                 int64_t block, int64_t stride, const clr_prepost* pp, double* out_lo, double* out_hi,
+                                 double* hull_lo, double* hull_hi, clr_stats* stats, int32_t keep_cap, int32_t flags);
 
 /* ---- DeepZ over explicit zonotopes ----------------------------------------------------------- */
 /* C: n x N centres; generators of cell i are columns col_off[i] .. col_off[i+1]-1 of G (n x col_off[N]) */
@@ -241,6 +257,39 @@ int32_t clr_rollout_plant(clr_ctx* ctx, const clr_net* net, const clr_prepost* p
                           double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end, double* U,
                           int32_t* naccept, int32_t* nreject, int32_t log_cap, int32_t* log_n, double* log_t,
                           double* log_u, int32_t flags);
+
+/* ---- several GPUs of one box behind one handle --------------------------------------------------
+ * Replaces, for a caller with more than one device, the same reference loops as clr_deepz_boxgrid / clr_rollout
+ * (src/solve.jl:153-166, :187-195; src/simulate.jl:98-140): the units (cells, trajectories) are independent, so device i
+ * takes a contiguous range of the unit ids with the network replicated and NO exchange step; one host thread and one
+ * stream per device for the duration of a call.  The only traffic between devices is the final gather of the per-device
+ * output hulls (2 m doubles each): peer copies (NVLink) to the first device, one min / max kernel there, one D2H copy.
+ * All data pointers are HOST pointers; results are in unit order exactly as from a single device (bit for bit when the
+ * neuron reordering is off; with it on every shard still uses the order derived from the whole split).
+ *   balance = 0: contiguous ranges of equal counts.  balance = 1: contiguous ranges whose boundaries are weighted by the
+ *   algorithmic cost (FLOPs per cell) that a statistics pilot over short ranges of 16 blocks per device measures; cached per
+ *   (network, split, range).  balance = 2: block-cyclic shards (device i takes the blocks i, i + G, ... of 1024 cells, see
+ *   clr_deepz_boxgrid_cyclic): equal time without a cost model -- the default to use when cell costs vary over the split.
+ *   The results are in cell order in every mode.  shard_bounds (n_devices + 1; ids for modes 0 / 1, cumulative shard sizes
+ *   for mode 2) and shard_ms (device time per shard) may be NULL. */
+typedef struct clr_multi clr_multi;
+typedef struct clr_multi_net clr_multi_net;
+int32_t clr_create_multi(const int32_t* devices, int32_t n_devices, clr_multi** out);
+void clr_destroy_multi(clr_multi* mc);
+int32_t clr_multi_size(const clr_multi* mc);
+clr_ctx* clr_multi_ctx(clr_multi* mc, int32_t i);           /* the per-device context (tuning knobs, launch counts) */
+const char* clr_multi_last_error(const clr_multi* mc);
+int32_t clr_multi_net_upload(clr_multi* mc, int32_t n_layers, const int32_t* dims, const int32_t* act,
+                             const double* const* W, const double* const* b, clr_multi_net** out);
+void clr_multi_net_free(clr_multi_net* net);
+int32_t clr_multi_deepz_boxgrid(clr_multi* mc, const clr_multi_net* net, int32_t n, const int32_t* partition,
+                                const double* centers, const double* radii, int64_t cell_begin, int64_t cell_count,
+                                const clr_prepost* pp, double* out_lo, double* out_hi, double* hull_lo, double* hull_hi,
+                                clr_stats* stats, int32_t balance, int64_t* shard_bounds, double* shard_ms);
+int32_t clr_multi_rollout(clr_multi* mc, const clr_multi_net* net, const clr_prepost* pp, int32_t plant, int32_t n_state,
+                          int32_t n_dist, int32_t n_ctrl, int64_t N, int32_t iters, const double* x0, const double* Wd, double t0,
+                          double tau, double T, int32_t alg, double abstol, double reltol, int32_t substeps, int32_t pow_mode,
+                          double* X_end, double* U, int32_t* naccept, int32_t* nreject);
 
 #ifdef __cplusplus
 }

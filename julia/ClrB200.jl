@@ -19,9 +19,14 @@ mutable struct Context
         rc = ccall((:clr_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, out)
         rc == 0 || error(unsafe_string(ccall((:clr_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
         ctx = new(out[])
-        finalizer(c -> ccall((:clr_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.h), ctx)
+        finalizer(close, ctx)
         return ctx
     end
+end
+function Base.close(c::Context)
+    c.h == C_NULL || ccall((:clr_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.h)
+    c.h = C_NULL
+    return nothing
 end
 
 function check(ctx::Context, rc::Int32)
@@ -33,9 +38,17 @@ end
 
 act_id(::Id) = Int32(0); act_id(::ReLU) = Int32(1); act_id(::Sigmoid) = Int32(2); act_id(::Tanh) = Int32(3)
 
-struct DeviceNetwork
+# clr_net: freed by its own finalizer; it holds its Context so that the context outlives the network (clr_net_free is also
+# safe after clr_destroy: the library keeps the device id in the clr_net, not a pointer into the context)
+mutable struct DeviceNetwork
     h::Ptr{Cvoid}
     net::FeedforwardNetwork
+    ctx::Context
+    function DeviceNetwork(h, net, ctx)
+        d = new(h, net, ctx)
+        finalizer(x -> (x.h == C_NULL || ccall((:clr_net_free, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), d)
+        return d
+    end
 end
 
 function upload(ctx::Context, net::FeedforwardNetwork)
@@ -50,7 +63,7 @@ function upload(ctx::Context, net::FeedforwardNetwork)
                          (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Ref{Ptr{Cvoid}}),
                          ctx.h, length(Ws), dims, acts, Wp, bp, out))
     end
-    return DeviceNetwork(out[], net)
+    return DeviceNetwork(out[], net, ctx)
 end
 
 # clr_prepost, field for field
@@ -75,7 +88,11 @@ function BoxGrid(X, partition::AbstractVector{<:Integer})
     cs = Float64[]; rs = Float64[]
     for (i, m) in enumerate(partition)
         r = R[i] / m
-        append!(cs, m == 1 ? [c[i]] : collect(range(c[i] - R[i] + r; step=2r, length=m)))   # LazySets' split
+        lo = c[i] - R[i]
+        # LazySets' split: block centres are range(lo + r; step=2r, length=m); a single block has the centre lo + R (not c:
+        # the two can differ by one ulp).  The Python mirror (splitters.py) emulates Julia's range with exact rationals; it
+        # has not been checked against a real Julia (tests/golden/dump_reference.jl produces the tables that would).
+        append!(cs, m == 1 ? [lo + R[i]] : collect(range(lo + r; step=2r, length=m)))
         append!(rs, fill(m == 1 ? R[i] : r, m))
     end
     return BoxGrid(Int32.(partition), cs, rs)
@@ -186,6 +203,164 @@ function compile_plant(ctx::Context, n_state::Integer, n_dist::Integer, n_ctrl::
     check(ctx, ccall((:clr_plant_compile, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Cstring, Ref{Ptr{Cvoid}}),
                      ctx.h, n_state, n_dist, n_ctrl, rhs_body, out))
     return out[]
+end
+
+"`forward(x, network)` + pre/post-processing for a batch of points (src/simulate.jl:101-106): X is nx x N, returns m x N."
+function forward_points(ctx::Context, dnet::DeviceNetwork, pp::PrePost, X::Matrix{Float64}, m::Integer)
+    nx, N = size(X)
+    U = Matrix{Float64}(undef, m, N)
+    check(ctx, ccall((:clr_forward_points, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ref{PrePost}, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Int32),
+                     ctx.h, dnet.h, pp, nx, N, X, U, 0))
+    return U
+end
+
+"""
+The output sets U of the last `keep_cap > 0` run (src/solve.jl:213 before the box of :214-216): generator counts (N),
+centres (m x N), generators (m x keep_cap x N, reference column order, zero padded).
+"""
+function fetch_zonotopes(ctx::Context, m::Integer, N::Integer, keep_cap::Integer)
+    ncols = Vector{Int32}(undef, N); c = Matrix{Float64}(undef, m, N); G = Array{Float64}(undef, m, keep_cap, N)
+    check(ctx, ccall((:clr_deepz_fetch_zonotopes, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}), ctx.h, ncols, c, G))
+    return ncols, c, G
+end
+
+"Full output zonotopes of a batch of zonotope cells: `[Zonotope(c[:, i], G[:, 1:ncols[i], i]) for i]` is `forward(X_i, net, DeepZ())`."
+function controller_forward_zonotopes(ctx::Context, dnet::DeviceNetwork, Zs::AbstractVector{<:Zonotope}, pp::PrePost, m::Integer,
+                                      keep_cap::Integer)
+    n = dim(first(Zs)); N = length(Zs)
+    C = reduce(hcat, center.(Zs)); off = Int64[0; cumsum(ngens.(Zs))]; G = reduce(hcat, genmat.(Zs))
+    lo = Matrix{Float64}(undef, m, N); hi = similar(lo)
+    check(ctx, ccall((:clr_deepz_zonotopes, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ref{PrePost},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Int32, Int32),
+                     ctx.h, dnet.h, n, N, C, off, G, pp, lo, hi, C_NULL, C_NULL, C_NULL, keep_cap, 2))
+    ncols, c, Gk = fetch_zonotopes(ctx, m, N, keep_cap)
+    return [Zonotope(c[:, i], Gk[:, 1:ncols[i], i]) for i in 1:N]
+end
+
+"`clr_rollout_plant`: the period loop of `simulate` for a plant compiled with `compile_plant` (same arguments as `rollout`)."
+function rollout_plant(ctx::Context, dnet::DeviceNetwork, pp::PrePost, plant::Ptr{Cvoid}, x0::Matrix{Float64}, Wd, t0, τ, T, iters;
+                       n_ctrl::Integer, abstol=1e-6, reltol=1e-3, counts::Bool=false)
+    ns, N = size(x0)
+    Xend = Array{Float64}(undef, ns, N, iters); U = Array{Float64}(undef, n_ctrl, N, iters)
+    na = counts ? Matrix{Int32}(undef, N, iters) : C_NULL
+    check(ctx, ccall((:clr_rollout_plant, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ref{PrePost}, Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Ptr{Float64},
+                      Float64, Float64, Float64, Int32, Float64, Float64, Int32, Int32, Ptr{Float64}, Ptr{Float64},
+                      Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int32),
+                     ctx.h, dnet.h, pp, plant, N, iters, x0, Wd === nothing ? C_NULL : Wd,
+                     t0, τ, T, 0, abstol, reltol, 4, 1, Xend, U, na, C_NULL, 0, C_NULL, C_NULL, C_NULL, 0))
+    return Xend, U, na
+end
+free_plant(p::Ptr{Cvoid}) = ccall((:clr_plant_free, LIB), Cvoid, (Ptr{Cvoid},), p)
+
+"""
+`rollout` with the accepted steps of every period logged (the `ODESolution.t` / `.u` of src/simulate.jl:129-136, which
+`plot_simulation!` reads): returns Xend, U, the step counts (N x iters), times (log_cap x N x iters) and extended states
+(n_ext x log_cap x N x iters).
+"""
+function rollout_logged(ctx::Context, dnet::DeviceNetwork, pp::PrePost, plant::Integer, x0::Matrix{Float64}, Wd, t0, τ, T, iters;
+                        n_dist::Integer, n_ctrl::Integer, abstol=1e-6, reltol=1e-3, log_cap::Integer=64)
+    ns, N = size(x0); ne = ns + n_dist + n_ctrl
+    Xend = Array{Float64}(undef, ns, N, iters); U = Array{Float64}(undef, n_ctrl, N, iters)
+    ln = Matrix{Int32}(undef, N, iters); lt = Array{Float64}(undef, log_cap, N, iters); lu = Array{Float64}(undef, ne, log_cap, N, iters)
+    check(ctx, ccall((:clr_rollout, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ref{PrePost}, Int32, Int32, Int32, Int32, Int64, Int32, Ptr{Float64}, Ptr{Float64},
+                      Float64, Float64, Float64, Int32, Float64, Float64, Int32, Int32, Ptr{Float64}, Ptr{Float64},
+                      Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int32),
+                     ctx.h, dnet.h, pp, plant, ns, n_dist, n_ctrl, N, iters, x0, n_dist > 0 ? Wd : C_NULL,
+                     t0, τ, T, 0, abstol, reltol, 4, 1, Xend, U, C_NULL, C_NULL, log_cap, ln, lt, lu, 0))
+    return Xend, U, ln, lt, lu
+end
+
+# ---- tuning / diagnostics ------------------------------------------------------------------------------------------
+synchronize(ctx::Context) = check(ctx, ccall((:clr_synchronize, LIB), Int32, (Ptr{Cvoid},), ctx.h))
+stream(ctx::Context) = ccall((:clr_stream, LIB), Ptr{Cvoid}, (Ptr{Cvoid},), ctx.h)
+launch_count(ctx::Context) = ccall((:clr_launch_count, LIB), Int64, (Ptr{Cvoid},), ctx.h)
+set_tile_cells!(ctx::Context, cells::Integer) = check(ctx, ccall((:clr_set_tile_cells, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, cells))
+set_reorder!(ctx::Context, on::Bool) = check(ctx, ccall((:clr_set_reorder, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, on))
+set_profiling!(ctx::Context, on::Bool) = check(ctx, ccall((:clr_set_profiling, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, on))
+function last_pass_info(ctx::Context)
+    ms = zeros(3); retried = Ref{Int64}(0); big = Ref{Int64}(0)
+    check(ctx, ccall((:clr_last_pass_info, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}, Ref{Int64}), ctx.h, ms, retried, big))
+    return ms, retried[], big[]
+end
+function measure_fp64_peak(ctx::Context, ms::Real=20.0)
+    out = Ref{Float64}(0.0)
+    check(ctx, ccall((:clr_measure_fp64_peak, LIB), Int32, (Ptr{Cvoid}, Float64, Ref{Float64}), ctx.h, ms, out))
+    return out[]
+end
+function device_alloc(ctx::Context, bytes::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:clr_device_alloc, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.h, bytes, out))
+    return out[]
+end
+device_free(ctx::Context, p::Ptr{Cvoid}) = check(ctx, ccall((:clr_device_free, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, p))
+memcpy_h2d(ctx::Context, dst::Ptr{Cvoid}, src::Array) =
+    GC.@preserve src check(ctx, ccall((:clr_memcpy_h2d, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), ctx.h, dst, pointer(src), sizeof(src)))
+memcpy_d2h(ctx::Context, dst::Array, src::Ptr{Cvoid}) =
+    GC.@preserve dst check(ctx, ccall((:clr_memcpy_d2h, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), ctx.h, pointer(dst), src, sizeof(dst)))
+
+# ---- several GPUs behind one handle (clr_create_multi) ------------------------------------------------------------
+mutable struct MultiContext
+    h::Ptr{Cvoid}
+    function MultiContext(devices::AbstractVector{<:Integer})
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        devs = Int32.(devices)
+        rc = ccall((:clr_create_multi, LIB), Int32, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devs, length(devs), out)
+        rc == 0 || error(unsafe_string(ccall((:clr_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        m = new(out[])
+        finalizer(x -> (x.h == C_NULL || ccall((:clr_destroy_multi, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), m)
+        return m
+    end
+end
+Base.length(mc::MultiContext) = Int(ccall((:clr_multi_size, LIB), Int32, (Ptr{Cvoid},), mc.h))
+function mcheck(mc::MultiContext, rc::Int32)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:clr_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), mc.h))
+    (rc == -1 || rc == -3) ? throw(ArgumentError(msg)) : error("libclr_b200 ($rc): $msg")
+end
+mutable struct MultiNetwork
+    h::Ptr{Cvoid}
+    mc::MultiContext
+end
+function upload(mc::MultiContext, net::FeedforwardNetwork)
+    Ws = [Matrix{Float64}(L.weights) for L in net.layers]; bs = [Vector{Float64}(L.bias) for L in net.layers]
+    dims = Int32[size(Ws[1], 2); [size(W, 1) for W in Ws]]; acts = Int32[act_id(L.activation) for L in net.layers]
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve Ws bs begin
+        Wp = [pointer(W) for W in Ws]; bp = [pointer(b) for b in bs]
+        mcheck(mc, ccall((:clr_multi_net_upload, LIB), Int32,
+                         (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Ref{Ptr{Cvoid}}),
+                         mc.h, length(Ws), dims, acts, Wp, bp, out))
+    end
+    mn = MultiNetwork(out[], mc)
+    finalizer(x -> (x.h == C_NULL || ccall((:clr_multi_net_free, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), mn)
+    return mn
+end
+"All cells of a split over every device of `mc` (block-cyclic shards by default), boxes in cell order, hull of all cells."
+function controller_forward_boxes(mc::MultiContext, mn::MultiNetwork, g::BoxGrid, pp::PrePost, m::Integer; balance::Integer=2)
+    N = length(g)
+    lo = Matrix{Float64}(undef, m, N); hi = similar(lo); hl = Vector{Float64}(undef, m); hh = similar(hl)
+    mcheck(mc, ccall((:clr_multi_deepz_boxgrid, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ref{PrePost},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Float64}),
+                     mc.h, mn.h, length(g.partition), g.partition, g.centers, g.radii, 0, N, pp, lo, hi, hl, hh, C_NULL, balance,
+                     C_NULL, C_NULL))
+    return lo, hi, hl, hh
+end
+"`rollout` with the trajectories sharded over every device of `mc`."
+function rollout(mc::MultiContext, mn::MultiNetwork, pp::PrePost, plant::Integer, x0::Matrix{Float64}, Wd, t0, τ, T, iters;
+                 n_dist::Integer, n_ctrl::Integer, abstol=1e-6, reltol=1e-3)
+    ns, N = size(x0)
+    Xend = Array{Float64}(undef, ns, N, iters); U = Array{Float64}(undef, n_ctrl, N, iters)
+    mcheck(mc, ccall((:clr_multi_rollout, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ref{PrePost}, Int32, Int32, Int32, Int32, Int64, Int32, Ptr{Float64}, Ptr{Float64},
+                      Float64, Float64, Float64, Int32, Float64, Float64, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+                     mc.h, mn.h, pp, plant, ns, n_dist, n_ctrl, N, iters, x0, n_dist > 0 ? Wd : C_NULL, t0, τ, T, 0, abstol, reltol,
+                     4, 1, Xend, U, C_NULL, C_NULL))
+    return Xend, U
 end
 
 end # module

@@ -125,3 +125,29 @@ def test_splits_with_more_than_2_pow_32_cells(ctx):
         c, r = g.cell(begin + 5)
         u = ctx.forward_points(dn, c[None, :], post=("shift", -10.0))[0, 0]
         assert got["lo"][5, 0] - 1e-12 <= u <= got["hi"][5, 0] + 1e-12
+
+
+def test_block_cyclic_shards_reassemble_to_the_contiguous_result(ctx, c4):
+    """clr_deepz_boxgrid_cyclic: rank r of G takes the blocks r, r + G, ... of `block` cells; the shards put back in id order
+    equal one contiguous call bit for bit (same pilot order for every shard: it is derived from the whole split)."""
+    from clr_b200 import workloads
+    net, on = c4
+    dn = ctx.upload(net)
+    g = workloads.c4_grid("mixed")
+    first, N, G, blk = 250000, 70000, 3, 1024
+    full = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=first, cell_count=N, stats=False)
+    lo = np.full((N, 1), np.nan)
+    hi = np.full((N, 1), np.nan)
+    nb = (N + blk - 1) // blk
+    for r in range(G):
+        ids = np.concatenate([np.arange(j * blk, min(N, (j + 1) * blk)) for j in range(r, nb, G)])
+        part = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=first + r * blk, cell_count=len(ids), stats=False,
+                                 block=blk, stride=G * blk, hull=True)
+        lo[ids], hi[ids] = part["lo"], part["hi"]
+        assert part["hull_lo"][0] == part["lo"].min()
+    assert np.array_equal(lo, full["lo"]) and np.array_equal(hi, full["hi"])
+    from clr_b200 import runtime
+    with pytest.raises(runtime.ClrArgumentError):      # the last block would lie beyond the split
+        ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=10 ** 6 - 2000, cell_count=2000, block=1024, stride=4096)
+    with pytest.raises(runtime.ClrArgumentError):
+        ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=0, cell_count=10, block=8, stride=4)

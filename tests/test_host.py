@@ -226,3 +226,28 @@ def test_runtime_plant_source_compiles_without_a_device():
     assert "no_such_symbol" in str(e.value)
     with pytest.raises(runtime.ClrArgumentError):
         runtime.CompiledPlant(None, 0, 0, 1, ok)
+
+
+def test_cost_weighted_bounds():
+    """parallel.bounds_from_costs: contiguous shards of equal estimated cost."""
+    from clr_b200 import parallel
+    edges = [0, 100, 200, 300, 400]
+    assert parallel.bounds_from_costs(edges, [1, 1, 1, 1], 4) == [0, 100, 200, 300, 400]
+    assert parallel.bounds_from_costs(edges, [1, 1, 1, 1], 2) == [0, 200, 400]
+    b = parallel.bounds_from_costs(edges, [3, 1, 1, 1], 2)            # total 600: half = 300 = the whole first block
+    assert b == [0, 100, 400]
+    b = parallel.bounds_from_costs(edges, [1, 1, 1, 3], 3)            # total 600, thirds at 200 and 400 cost units
+    assert b == [0, 200, 333, 400]
+    b = parallel.bounds_from_costs([10, 20], [0.0], 3)                # no cost information: equal counts
+    assert b == [10, 13, 16, 20]
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        B, W = int(rng.integers(1, 40)), int(rng.integers(1, 9))
+        e = np.concatenate([[0], np.cumsum(rng.integers(1, 1000, B))]).tolist()
+        c = rng.uniform(0.5, 2.0, B).tolist()
+        b = parallel.bounds_from_costs(e, c, W)
+        assert len(b) == W + 1 and b[0] == e[0] and b[-1] == e[-1] and all(x <= y for x, y in zip(b, b[1:]))
+        # shard costs within one block's worth of each other
+        cum = lambda x: sum(ci * (min(x, e[i + 1]) - e[i]) for i, ci in enumerate(c) if x > e[i])
+        costs = [cum(b[r + 1]) - cum(b[r]) for r in range(W)]
+        assert max(costs) - min(costs) <= 2.0 * 1000 + 1e-9
