@@ -21,7 +21,7 @@ SYMBOLS = [
     "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_boxgrid_cyclic", "clr_deepz_zonotopes", "clr_deepz_zonotopes_padded",
     "clr_deepz_fetch_zonotopes", "clr_deepz_fetch_reduced", "clr_project_oa", "clr_forward_points", "clr_rollout",
     "clr_plant_compile", "clr_plant_free", "clr_rollout_plant",
-    "clr_create_multi", "clr_destroy_multi", "clr_multi_size", "clr_multi_ctx", "clr_multi_last_error",
+    "clr_split_zonotopes", "clr_sign_split", "clr_create_multi", "clr_destroy_multi", "clr_multi_size", "clr_multi_ctx", "clr_multi_last_error",
     "clr_multi_net_upload", "clr_multi_net_free", "clr_multi_deepz_boxgrid", "clr_multi_rollout",
 ]
 
@@ -113,6 +113,10 @@ def lib():
     L.clr_rollout_plant.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, dbl, dbl, dbl, i32, dbl, dbl, i32, i32, vp, vp, vp, vp, i32,
                                     vp, vp, vp, i32]
     L.clr_rollout_plant.restype = i32
+    L.clr_split_zonotopes.argtypes = [vp, i32, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32]
+    L.clr_split_zonotopes.restype = i32
+    L.clr_sign_split.argtypes = [vp, i64, vp, vp, vp, vp, vp, C.POINTER(i64), i32]
+    L.clr_sign_split.restype = i32
     L.clr_create_multi.argtypes = [vp, i32, C.POINTER(vp)]
     L.clr_create_multi.restype = i32
     L.clr_destroy_multi.argtypes = [vp]

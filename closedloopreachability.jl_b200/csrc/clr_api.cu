@@ -20,6 +20,7 @@
 #include "rollout.cuh"
 #include "reduce.cuh"
 #include "project.cuh"
+#include "split.cuh"
 
 #define CLR_BOUNCE_BYTES (1u << 20)  // pinned bounce buffer of the small-call path
 #define CLR_BOUNCE_IN_MAX (256u << 10)
@@ -51,7 +52,6 @@ struct Compiled {            // one (network, pre/post-processing) pair on the d
     std::vector<HostLayer> layers_folded;     // the layer list this image was built from
     Compiled* perm = nullptr;                 // the same network with reordered neurons (see compile_net_reordered)
     std::vector<unsigned char> pilot_key;     // the split `perm` was derived for: the pilot is skipped while it stays the same
-    int pilot_peak_cols = 0;                  // columns per cell at the widest layer, seen by that pilot (picks the wide relaxation)
 };
 
 }  // namespace
@@ -503,8 +503,17 @@ namespace {
 // and the shared memory at hand instead of for the largest supported tile (64 cells x 512 rows x 2048 columns) -- every KB
 // saved is column store.  ncol_need > 0 fixes the position table (global-store pass: cells wider than an SM's store).
 // Returns the bytes of dynamic shared memory in front of the column store.
-size_t dz_geom(const DevNet& D, bool stats, size_t smem_total, int ncol_need, DeepzSched& sp) {
-    const size_t fixed = dz_meta_bytes(stats);
+#define CLR_ASTAGE_MAX (48u << 10)   // largest W-fragment image staged in shared memory by TMA (wide-K layers)
+size_t dz_geom(const DevNet& D, bool stats, size_t smem_total, int ncol_need, DeepzSched& sp, int ksreg = 32) {
+    const size_t fixed0 = dz_meta_bytes(stats);
+    // TMA staging area of the largest wide-K fragment image that fits the budget (DeepzSched::astage_*), behind the fixed metadata
+    size_t astage = 0;
+    for (int l = 0; l < D.L; l++) {
+        const size_t img = (size_t)D.layer[l].rblocks * D.layer[l].ksteps * 256;
+        if (D.layer[l].ksteps > ksreg && img <= CLR_ASTAGE_MAX) astage = std::max(astage, img);
+    }
+    sp.astage_off = (int)fixed0; sp.astage_bytes = (int)astage;
+    const size_t fixed = fixed0 + astage;
     sp.mask_words = std::max(1, (D.max_rows + 31) / 32);
     sp.mask_stride = sp.mask_words | 1;
     const long long avail_cols = smem_total > fixed ? (long long)((smem_total - fixed) / 8 / (size_t)D.max_pitch) : 0;
@@ -518,7 +527,7 @@ size_t dz_geom(const DevNet& D, bool stats, size_t smem_total, int ncol_need, De
 }
 
 int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int grid, int threads, size_t smem,
-                 const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp, bool wide = false) {
+                 const DeepzInput& in, const DeepzOutput& out, const DeepzSched& sp) {
     cudaError_t e;
     const int ksreg = c->ksreg;
     const DevNet* net = c->dev;
@@ -528,12 +537,11 @@ int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int g
         full = full || d.act == CLR_ACT_SIGMOID || d.act == CLR_ACT_TANH || d.ksteps > ksreg;
     }
     full = full || !c->inplace;                 // two-buffer products (a layer wider than 128 neurons)
-    wide = wide && sp.wide && (global || !full);   // the instantiations that exist (deepz_ks.inc)
     switch (ksreg) {   // one translation unit per KSREG (deepz_ks*.cu), so that the instantiations compile in parallel
-        case 8: e = launch_deepz_ks8(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        case 16: e = launch_deepz_ks16(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        case 25: e = launch_deepz_ks25(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        default: e = launch_deepz_ks32(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 8: e = launch_deepz_ks8(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 16: e = launch_deepz_ks16(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 25: e = launch_deepz_ks25(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        default: e = launch_deepz_ks32(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
     }
     if (e != cudaSuccess) return fail(ctx, CLR_ERR_CUDA, "DeepZ kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
@@ -572,8 +580,9 @@ int reorder_for_grid(clr_ctx* ctx, Compiled* c, const DeepzInput& in_full, long 
     DeepzOutput out{};
     out.liveCount = ctx->d_live;
     DeepzSched sp{};
-    const size_t meta = dz_geom(D, false, (size_t)ctx->smem_optin, 0, sp);
-    sp.cap = (int)(((size_t)ctx->smem_optin - meta) / 8);
+    const size_t smem_cta = ((size_t)ctx->smem_optin + 1024) / DZ_CTAS - 1024;      // shared memory of one CTA
+    const size_t meta = dz_geom(D, false, smem_cta, 0, sp, c->ksreg);
+    sp.cap = (int)((smem_cta - meta) / 8);
     sp.tile_cells = 4;                    // fixed tiles: which cells a tile drops must not depend on the scheduling,
                                           // or the order (and the last bits of the results) would vary from call to call
     sp.inplace = c->inplace;
@@ -582,14 +591,12 @@ int reorder_for_grid(clr_ctx* ctx, Compiled* c, const DeepzInput& in_full, long 
     sp.big_list = ctx->d_big;             // overflowing cells are simply not sampled (the list is reset by the real run)
     DevCallState* saved = ctx->d_state;
     ctx->d_state = ctx->d_state2;
-    int rc = launch_deepz(ctx, false, false, c, (int)std::min<long long>(ctx->sms, S), DZ_THREADS, meta + (size_t)sp.cap * 8,
+    int rc = launch_deepz(ctx, false, false, c, (int)std::min<long long>((long long)ctx->sms * DZ_CTAS, S), DZ_THREADS, meta + (size_t)sp.cap * 8,
                           in, out, sp);
     ctx->d_state = saved;
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->h_live, ctx->d_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state2, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    c->pilot_peak_cols = ctx->h_state->max_p_out;
     std::vector<std::vector<int>> order((size_t)D.L);
     bool changed = false;
     for (int l = 0; l + 1 < D.L; l++) {
@@ -608,9 +615,8 @@ int reorder_for_grid(clr_ctx* ctx, Compiled* c, const DeepzInput& in_full, long 
 }
 
 // Shared driver of clr_deepz_boxgrid / clr_deepz_zonotopes once `in` points at device inputs.
-#define CLR_WIDE_COLS 96   // main pass: cells of this many columns (pilot / input) take the several-threads-per-neuron relaxation
 int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max, double* out_lo, double* out_hi,
-              double* hull_lo, double* hull_hi, clr_stats* stats, int keep_cap, int flags, int peak_cols_hint = 0) {
+              double* hull_lo, double* hull_hi, clr_stats* stats, int keep_cap, int flags) {
     const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
     const bool want_stats = stats != nullptr && !(flags & CLR_FLAG_NO_STATS);
     const DevNet& D = c->host;
@@ -643,16 +649,23 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     // come back in one copy from one contiguous region [hull | lo | hi] of the bounce buffer.
     size_t fast_off = 0, fast_bytes = 0;
     bool fast = false;
+    // The scheduler state travels the same way: its zeroed image goes up with the inputs (no memset call) and comes back with
+    // the results (no copy of its own): one region [state | hull | lo | hi] -- four driver calls per step in all.
+    const size_t sb = (sizeof(DevCallState) + 255) & ~(size_t)255;
+    struct StateSwap { clr_ctx* c; DevCallState* saved; ~StateSwap() { c->d_state = saved; } } swap_guard{ctx, ctx->d_state};
     if (!dev_io && ctx->bounce_open && keep_cap == 0) {
         const size_t hb = want_hull ? sizeof(double) * 2 * (size_t)m : 0;
         const size_t ob = (out_lo && out_hi) ? sizeof(double) * (size_t)m * (size_t)N : 0;
-        double* hseed = (double*)bounce_take(ctx, hb + 2 * ob + 16, &fast_off);
-        if (hseed) {
+        unsigned char* base = (unsigned char*)bounce_take(ctx, sb + hb + 2 * ob + 16, &fast_off);
+        if (base) {
             fast = true;
-            fast_bytes = hb + 2 * ob;
+            fast_bytes = sb + hb + 2 * ob;
+            memset(base, 0, sizeof(DevCallState));
+            double* hseed = (double*)(base + sb);
             for (int i = 0; want_hull && i < m; i++) { hseed[i] = INFINITY; hseed[m + i] = -INFINITY; }
-            ctx->bounce_used = fast_off + hb;          // only the seed has to go up
-            double* dbase = (double*)(ctx->d_bounce + fast_off);
+            ctx->bounce_used = fast_off + sb + hb;     // the state and the seed have to go up
+            ctx->d_state = (DevCallState*)(ctx->d_bounce + fast_off);
+            double* dbase = (double*)(ctx->d_bounce + fast_off + sb);
             if (want_hull) { out.hull_lo = dbase; out.hull_hi = dbase + m; }
             if (ob) { out.out_lo = dbase + 2 * (want_hull ? m : 0); out.out_hi = out.out_lo + (size_t)m * N; }
         }
@@ -696,16 +709,16 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         CU(cudaMalloc((void**)&ctx->d_big, sizeof(long long) * (size_t)N));
         ctx->list_cap = N;
     }
-    CU(cudaMemsetAsync(ctx->d_state, 0, sizeof(DevCallState), ctx->stream));
+    if (!fast) CU(cudaMemsetAsync(ctx->d_state, 0, sizeof(DevCallState), ctx->stream));
 
     const int threads = DZ_THREADS;
     // kept zonotopes need the zero-generator bookkeeping, which only the STATS instantiations carry
     const bool kstats = want_stats || keep_cap > 0;
-    const size_t smem_total = (size_t)ctx->smem_optin;
+    const size_t smem_total = ((size_t)ctx->smem_optin + 1024) / DZ_CTAS - 1024;      // shared memory of one CTA
     DeepzSched sp{};
     for (int l = 0; l < D.L; l++)      // every sigmoid / tanh neuron appends a generator (unless its bounds coincide)
         if (D.layer[l].act == CLR_ACT_SIGMOID || D.layer[l].act == CLR_ACT_TANH) sp.grow_cols += D.layer[l].m;
-    const size_t meta = dz_geom(D, kstats, smem_total, 0, sp);
+    const size_t meta = dz_geom(D, kstats, smem_total, 0, sp, c->ksreg);
     if (smem_total < meta + 8 * 1024) return fail(ctx, CLR_ERR_CUDA, "device has too little shared memory");
     sp.cap = (int)((smem_total - meta) / 8);
     sp.tile_cells = ctx->tile_cells;
@@ -717,32 +730,28 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         const DevLayer& lt = D.layer[D.L - 1];
         sp.fuse_tail = D.L >= 2 && lt.act == CLR_ACT_ID && lt.m <= 4 && lt.n <= 4 && !lt.remove_zero && keep_cap == 0;
     }
-    sp.wide = sp.grow_cols == 0;      // networks whose cell widths are data dependent (ReLU); sigmoid / tanh tiles are sized exactly
     sp.retry_list = ctx->d_retry;
     sp.big_list = ctx->d_big;
     sp.workspace = nullptr;
-    int grid = (int)std::min<long long>(ctx->sms, N);
+    int grid = (int)std::min<long long>((long long)ctx->sms * DZ_CTAS, N);
     int rc;
     sp.pass = 0;
     ctx->pass_ms[0] = ctx->pass_ms[1] = ctx->pass_ms[2] = 0.f;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    bool wide_main = std::max(peak_cols_hint, 1 + p0max) >= CLR_WIDE_COLS;
-    if (const char* force = getenv("CLR_B200_WIDE")) wide_main = force[0] == '1';     // A/B switch of profiles/ab_bench.py
-    if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp, wide_main))) return rc;
+    if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
     bool fast_done = false;
     if (fast) {
         // one round trip: scheduler state and results together; the retry pass only runs when a tile overflowed
-        CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
-        if (fast_bytes)
-            CU(cudaMemcpyAsync(ctx->h_bounce + fast_off, ctx->d_bounce + fast_off, fast_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_bounce + fast_off, ctx->d_bounce + fast_off, fast_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        memcpy(ctx->h_state, ctx->h_bounce + fast_off, sizeof(DevCallState));
         fast_done = ctx->h_state->n_retry == 0 && ctx->h_state->n_big == 0;
     }
     if (!fast || ctx->h_state->n_retry > 0) {
-        if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp, getenv("CLR_B200_WIDE") ? wide_main : true))) return rc;   // cells that overflowed a tile: wide
+        if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         // how many cells did not fit in shared memory at all?
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -759,15 +768,17 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         DeepzSched sg = sp;
         sg.pass = 2;
         const int stageW = std::max(clr_pad4(D.max_rows), 2 * D.n_in);
-        sg.cap = (wc + 8) * D.max_pitch * (c->inplace ? 1 : 2) + stageW + 64 + 4 * clr_pad4(D.max_rows);   // + the wide relaxation's scratch (DZ_WCH per row)
-        int gridg = (int)std::min<unsigned long long>((unsigned long long)ctx->sms, ctx->h_state->n_big);
-        size_t need = sizeof(double) * (size_t)gridg * sg.cap;
+        sg.cap = (wc + 8) * D.max_pitch * (c->inplace ? 1 : 2) + stageW + 64;
+        int gridg = (int)std::min<unsigned long long>((unsigned long long)ctx->sms * DZ_CTAS, ctx->h_state->n_big);
+        // sized for a full grid whatever n_big is: the number of such cells varies from call to call (cells at the edge of the
+        // capacity), and growing the workspace means a cudaFree + cudaMalloc in the middle of the step (7 ms per step in the mixed regime)
+        size_t need = sizeof(double) * (size_t)ctx->sms * DZ_CTAS * sg.cap;
         if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, need))) return rc;
         sg.workspace = ctx->d_ws;
-        const size_t metag = dz_geom(D, kstats, smem_total, wc + 8 + 40, sg);     // one wide cell per tile
+        const size_t metag = dz_geom(D, kstats, smem_total, wc + 8 + 40, sg, c->ksreg);     // one wide cell per tile
         if (metag > smem_total) return fail(ctx, CLR_ERR_CAPACITY, "a cell with %d columns exceeds the tile metadata", wc);
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        if ((rc = launch_deepz(ctx, true, kstats, c, gridg, threads, metag, in, out, sg, getenv("CLR_B200_WIDE") ? wide_main : true))) return rc;
+        if ((rc = launch_deepz(ctx, true, kstats, c, gridg, threads, metag, in, out, sg))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[3], ctx->stream));
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -796,11 +807,11 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
             CU(cudaMemcpyAsync(hull_hi, ctx->d_hull + m, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
         }
     } else if (fast) {
-        if (!fast_done && fast_bytes) {
+        if (!fast_done) {
             CU(cudaMemcpyAsync(ctx->h_bounce + fast_off, ctx->d_bounce + fast_off, fast_bytes, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         }
-        const double* hb = (const double*)(ctx->h_bounce + fast_off);
+        const double* hb = (const double*)(ctx->h_bounce + fast_off + sb);
         if (want_hull) { memcpy(hull_lo, hb, sizeof(double) * m); memcpy(hull_hi, hb + m, sizeof(double) * m); hb += 2 * m; }
         if (out_lo && out_hi) {
             memcpy(out_lo, hb, sizeof(double) * (size_t)m * N);
@@ -1097,7 +1108,6 @@ int32_t clr_deepz_boxgrid_cyclic(clr_ctx* ctx, const clr_net* net_c, int32_t n, 
     in.kind = 0; in.n = n; in.N = cell_count; in.cell_begin = cell_begin;
     in.cyc_blk = block; in.cyc_stride = stride;
     in.centers = (const double*)dc; in.radii = (const double*)dr;
-    int peak_hint = 0;
     if (ctx->reorder && keep_cap == 0 && cell_count >= CLR_REORDER_MIN_CELLS) {
         if (cell_count > ctx->list_cap) {       // the pilot borrows the large-cell list of the real run
             if (ctx->d_retry) CU(cudaFree(ctx->d_retry));
@@ -1114,11 +1124,9 @@ int32_t clr_deepz_boxgrid_cyclic(clr_ctx* ctx, const clr_net* net_c, int32_t n, 
         put(partition, sizeof(int32_t) * n);
         if (dev_io) { put(&centers, sizeof(centers)); put(&radii, sizeof(radii)); }
         else { put(centers, sizeof(double) * tab); put(radii, sizeof(double) * tab); }
-        Compiled* base = c;
         if ((rc = reorder_for_grid(ctx, c, in, total, n, sk, &c))) return rc;
-        peak_hint = base->pilot_peak_cols;
     }
-    return run_deepz(ctx, net, c, in, n, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags, peak_hint);
+    return run_deepz(ctx, net, c, in, n, out_lo, out_hi, hull_lo, hull_hi, stats, keep_cap, flags);
 }
 
 int32_t clr_deepz_zonotopes(clr_ctx* ctx, const clr_net* net_c, int32_t n, int64_t N, const double* C,
@@ -1238,7 +1246,7 @@ int32_t clr_deepz_fetch_reduced(clr_ctx* ctx, int32_t order, double* out_c, doub
     const size_t bc = sizeof(double) * m * N, bg = sizeof(double) * m * m * (size_t)order * N;
     ReduceArgs A;
     A.N = (long long)N; A.m = (int)m; A.cap = ctx->keep_cap; A.order = order;
-    A.keepN = ctx->d_keepN; A.keepC = ctx->d_keepC; A.keepG = ctx->d_keepG; A.error = ctx->d_err;
+    A.keepN = ctx->d_keepN; A.keepC = ctx->d_keepC; A.keepG = ctx->d_keepG; A.error = ctx->d_err; A.cap2 = 0;
     if (dev_io) { A.outC = out_c; A.outG = out_G; }
     else {
         int rc;
@@ -1246,7 +1254,10 @@ int32_t clr_deepz_fetch_reduced(clr_ctx* ctx, int32_t order, double* out_c, doub
         if ((rc = ensure(ctx, &ctx->d_io[7], &ctx->io_bytes[7], bg))) return rc;
         A.outC = (double*)ctx->d_io[6]; A.outG = (double*)ctx->d_io[7];
     }
-    const size_t smem = (size_t)RD_WARPS * A.cap * (sizeof(double) + sizeof(int));
+    int cap2 = 1;                       // the index array is sorted over the next power of two
+    while (cap2 < A.cap) cap2 <<= 1;
+    const size_t smem = (size_t)RD_WARPS * ((size_t)A.cap * sizeof(double) + (size_t)cap2 * sizeof(int));
+    A.cap2 = cap2;
     if (smem > (size_t)ctx->smem_optin) return fail(ctx, CLR_ERR_CAPACITY, "keep_cap = %d is too large for the order reduction", A.cap);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(reduce_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
@@ -1266,6 +1277,105 @@ int32_t clr_deepz_fetch_reduced(clr_ctx* ctx, int32_t order, double* out_c, doub
     if (err)
         return fail(ctx, CLR_ERR_DIM, "order-%d reduction needs at least %d generators per zonotope (the reference's reduce_order "
                     "indexes past the end there)", order, (int)m * (order - 1));
+    return 0;
+}
+
+int32_t clr_split_zonotopes(clr_ctx* ctx, int32_t n, int64_t N, const double* C, const double* G, const int32_t* ncols, int32_t cap,
+                            int32_t n_gens, const int32_t* gens, const int32_t* nparts, double* out_C, double* out_G,
+                            int32_t* out_ncols, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (n < 1 || N < 0 || cap < 0 || n_gens < 0 || (n_gens > 0 && (!gens || !nparts)))
+        return fail(ctx, CLR_ERR_ARG, "clr_split_zonotopes: bad argument");
+    int H = 0;
+    for (int i = 0; i < n_gens; i++) {
+        if (nparts[i] < 0) return fail(ctx, CLR_ERR_ARG, "nparts[%d] = %d", i, nparts[i]);
+        if (gens[i] < 0 || gens[i] >= cap) return fail(ctx, CLR_ERR_ARG, "generator index %d outside the capacity %d", gens[i], cap);
+        H += nparts[i];
+    }
+    if (H > 30) return fail(ctx, CLR_ERR_ARG, "%d halvings: 2^%d children per zonotope are not supported", H, H);
+    if (N == 0) return 0;
+    if (!C || !ncols || (cap > 0 && !G) || !out_C || !out_G || !out_ncols) return fail(ctx, CLR_ERR_ARG, "clr_split_zonotopes: NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    const size_t total = (size_t)N << H;
+    ctx->bounce_open = false;
+    int rc;
+    const void *dC, *dG, *dN, *dmeta;
+    std::vector<int> meta(2 * (size_t)std::max(n_gens, 1));
+    for (int i = 0; i < n_gens; i++) { meta[i] = gens[i]; meta[n_gens + i] = nparts[i]; }
+    if ((rc = stage_in(ctx, 0, C, sizeof(double) * (size_t)n * N, dev_io, &dC))) return rc;
+    if ((rc = stage_in(ctx, 1, ncols, sizeof(int32_t) * (size_t)N, dev_io, &dN))) return rc;
+    if ((rc = stage_in(ctx, 2, G, sizeof(double) * (size_t)n * cap * N, dev_io, &dG))) return rc;
+    if ((rc = stage_in(ctx, 3, meta.data(), sizeof(int) * meta.size(), false, &dmeta))) return rc;
+    SplitArgs A;
+    A.N = N; A.n = n; A.cap = cap; A.H = H; A.ng = n_gens;
+    A.C = (const double*)dC; A.G = (const double*)dG; A.ncols = (const int*)dN;
+    A.gens = (const int*)dmeta; A.nparts = (const int*)dmeta + n_gens; A.error = ctx->d_err;
+    const size_t bC = sizeof(double) * (size_t)n * total, bG = sizeof(double) * (size_t)n * cap * total, bN = sizeof(int) * total;
+    if (dev_io) { A.outC = out_C; A.outG = out_G; A.outN = out_ncols; }
+    else {
+        if ((rc = ensure(ctx, &ctx->d_io[5], &ctx->io_bytes[5], bC))) return rc;
+        if ((rc = ensure(ctx, &ctx->d_io[6], &ctx->io_bytes[6], bG ? bG : 8))) return rc;
+        if ((rc = ensure(ctx, &ctx->d_io[7], &ctx->io_bytes[7], bN))) return rc;
+        A.outC = (double*)ctx->d_io[5]; A.outG = (double*)ctx->d_io[6]; A.outN = (int*)ctx->d_io[7];
+    }
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    const size_t threads = total * 32;
+    split_zonotopes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    if (!dev_io) {
+        int err = 0;
+        CU(cudaMemcpyAsync(&err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_C, A.outC, bC, cudaMemcpyDeviceToHost, ctx->stream));
+        if (bG) CU(cudaMemcpyAsync(out_G, A.outG, bG, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_ncols, A.outN, bN, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (err) return fail(ctx, CLR_ERR_ARG, "a listed generator index is not smaller than the generator count of its zonotope");
+    }
+    return 0;
+}
+
+int32_t clr_sign_split(clr_ctx* ctx, int64_t N, const double* lo, const double* hi, double* out_lo, double* out_hi,
+                       int64_t* out_parent, int64_t* out_count, int32_t flags) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (N < 0 || !out_count) return fail(ctx, CLR_ERR_ARG, "clr_sign_split: bad argument");
+    const bool dev_io = flags & CLR_FLAG_DEVICE_IO;
+    if (N == 0) { if (!dev_io) *out_count = 0; return 0; }
+    if (!lo || !hi || !out_lo || !out_hi || !out_parent) return fail(ctx, CLR_ERR_ARG, "clr_sign_split: NULL buffer");
+    CU(cudaSetDevice(ctx->device));
+    ctx->bounce_open = false;
+    int rc;
+    const void *dlo, *dhi;
+    if ((rc = stage_in(ctx, 0, lo, sizeof(double) * (size_t)N, dev_io, &dlo))) return rc;
+    if ((rc = stage_in(ctx, 1, hi, sizeof(double) * (size_t)N, dev_io, &dhi))) return rc;
+    const long long nb = (N + SS_BLOCK - 1) / SS_BLOCK;
+    if ((rc = ensure(ctx, &ctx->d_io[3], &ctx->io_bytes[3], sizeof(long long) * (size_t)(nb + 1)))) return rc;
+    long long* bs = (long long*)ctx->d_io[3];
+    double *olo = out_lo, *ohi = out_hi;
+    long long* opar = (long long*)out_parent;
+    long long* ocnt = dev_io ? (long long*)out_count : bs + nb;
+    if (!dev_io) {
+        if ((rc = ensure(ctx, &ctx->d_io[5], &ctx->io_bytes[5], sizeof(double) * 2 * (size_t)N))) return rc;
+        if ((rc = ensure(ctx, &ctx->d_io[6], &ctx->io_bytes[6], sizeof(double) * 2 * (size_t)N))) return rc;
+        if ((rc = ensure(ctx, &ctx->d_io[7], &ctx->io_bytes[7], sizeof(long long) * 2 * (size_t)N))) return rc;
+        olo = (double*)ctx->d_io[5]; ohi = (double*)ctx->d_io[6]; opar = (long long*)ctx->d_io[7];
+    }
+    sign_count_kernel<<<(unsigned)nb, SS_BLOCK, 0, ctx->stream>>>(N, (const double*)dlo, (const double*)dhi, bs);
+    sign_scan_kernel<<<1, SS_BLOCK, 0, ctx->stream>>>(nb, bs, ocnt);
+    sign_scatter_kernel<<<(unsigned)nb, SS_BLOCK, 0, ctx->stream>>>(N, (const double*)dlo, (const double*)dhi, bs, olo, ohi, opar);
+    CU(cudaGetLastError());
+    ctx->launches += 3;
+    if (!dev_io) {
+        long long cnt = 0;
+        CU(cudaMemcpyAsync(&cnt, ocnt, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpyAsync(out_lo, olo, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_hi, ohi, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out_parent, opar, sizeof(long long) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *out_count = cnt;
+    }
     return 0;
 }
 
@@ -1300,9 +1410,14 @@ int32_t clr_project_oa(clr_ctx* ctx, int32_t n, int32_t order_t, int32_t n_monom
     }
     if (n_const != 1) return fail(ctx, CLR_ERR_ARG, "clr_project_oa: the exponent table needs exactly one constant monomial (has %d)", n_const);
     for (int k = 0; k < n_keep; k++) meta[(size_t)M + k] = vars[k];
+    // LazySets' remove_redundant_generators (CLR_FLAG_MERGE_REDUNDANT) needs every component: parallel columns are found in n dimensions
+    const bool merge = (flags & CLR_FLAG_MERGE_REDUNDANT) != 0;
+    if (merge && n > PJ_NMAX) return fail(ctx, CLR_ERR_DIM, "CLR_FLAG_MERGE_REDUNDANT supports at most %d variables", PJ_NMAX);
+    const int n_eval = merge ? n : n_keep;
+    if (merge) { meta.resize((size_t)M + n_keep + n); for (int v = 0; v < n; v++) meta[(size_t)M + n_keep + v] = v; }
     const size_t bcoef = sizeof(double) * (size_t)N * n * (order_t + 1) * M, brem = sizeof(double) * (size_t)N * n * 2;
     const size_t bC = sizeof(double) * (size_t)N * n_keep, bG = sizeof(double) * (size_t)N * 2 * n * n_keep;
-    const size_t bscr = sizeof(double) * (size_t)N * n_keep * (n + 2);
+    const size_t bscr = sizeof(double) * (size_t)N * (size_t)((flags & CLR_FLAG_MERGE_REDUNDANT) ? n : n_keep) * (n + 2);
     int rc;
     const void *dcoef, *drem, *ddt, *dmeta;
     if ((rc = stage_in(ctx, 0, coeffs, bcoef, dev_io, &dcoef))) return rc;
@@ -1310,8 +1425,9 @@ int32_t clr_project_oa(clr_ctx* ctx, int32_t n, int32_t order_t, int32_t n_monom
     if ((rc = stage_in(ctx, 2, dt, sizeof(double) * (size_t)N, dev_io, &ddt))) return rc;
     if ((rc = stage_in(ctx, 3, meta.data(), sizeof(int) * meta.size(), false, &dmeta))) return rc;
     ProjArgs A;
-    A.N = (long long)N; A.n = n; A.KT = order_t + 1; A.M = M; A.nkeep = n_keep; A.remove_zero = remove_zero_generators != 0;
-    A.cls = (const int*)dmeta; A.vars = (const int*)dmeta + M;
+    A.N = (long long)N; A.n = n; A.KT = order_t + 1; A.M = M; A.nkeep = n_eval; A.remove_zero = remove_zero_generators != 0;
+    A.cls = (const int*)dmeta; A.vars = merge ? (const int*)dmeta + M + n_keep : (const int*)dmeta + M;
+    A.merge = merge; A.nproj = n_keep; A.pvars = (const int*)dmeta + M;
     A.coeffs = (const double*)dcoef; A.rem = (const double*)drem; A.dt = (const double*)ddt;
     if ((rc = ensure(ctx, (void**)&ctx->d_ws, &ctx->ws_bytes, bscr))) return rc;
     A.scratch = ctx->d_ws;
@@ -1323,11 +1439,12 @@ int32_t clr_project_oa(clr_ctx* ctx, int32_t n, int32_t order_t, int32_t n_monom
         if ((rc = ensure(ctx, &ctx->d_io[7], &ctx->io_bytes[7], sizeof(int) * (size_t)N))) return rc;
         A.outC = (double*)ctx->d_io[5]; A.outG = (double*)ctx->d_io[6]; A.outN = (int*)ctx->d_io[7];
     }
-    const long long units = (long long)N * n_keep;
+    const long long units = (long long)N * n_eval;
     const int grid1 = (int)std::max<long long>(1, std::min<long long>((units + PJ_WARPS - 1) / PJ_WARPS, (long long)ctx->sms * 16));
     project_eval_kernel<<<grid1, PJ_WARPS * 32, 0, ctx->stream>>>(A);
     CU(cudaGetLastError());
-    project_pack_kernel<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(A);
+    if (merge) project_pack_merge_kernel<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(A);
+    else project_pack_kernel<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(A);
     CU(cudaGetLastError());
     ctx->launches += 2;
     if (!dev_io) {

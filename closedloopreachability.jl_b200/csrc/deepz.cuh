@@ -66,6 +66,36 @@ __device__ __forceinline__ void atomicMaxD(double* addr, double v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA (bulk async copy) staging of W fragments.  Layers whose K exceeds what a warp can keep in registers (K > 4 KSREG,
+// e.g. Unicycle's 500 -> 2 layer) read their A fragments once per k-step and column group; instead of fetching them from
+// L2 for every group, the layer's whole fragment image (rblocks x ksteps x 256 B) is copied to shared memory ONCE per
+// (tile, layer) by one thread with cp.async.bulk (SASS UBLKCP) and completed on an mbarrier; the k-loop then reads it with
+// conflict-free LDS.64.  Only when the image fits the staging area the host reserved (DeepzSched::astage_bytes).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned dz_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dz_mbar_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(dz_smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+// one thread: copy `bytes` (multiple of 16) global -> shared, completion counted on `bar`
+__device__ __forceinline__ void dz_tma_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // earlier generic reads of dst are ordered before the async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(dz_smem_u32(bar)), "r"(bytes) : "memory");
+    for (unsigned o = 0; o < bytes; o += 32768u) {
+        const unsigned n = min(32768u, bytes - o);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(dz_smem_u32((const char*)dst + o)), "l"((const char*)src + o), "r"(n), "r"(dz_smem_u32(bar)) : "memory");
+    }
+}
+__device__ __forceinline__ void dz_mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(dz_smem_u32(bar)), "r"(phase) : "memory");
+    } while (!ok);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Warp -> (row block, column part) mapping of the layer product.  16 warps sit on 4 SM sub-partitions
 // (warp w on w % 4); the DMMA rate is per sub-partition, so the row blocks are dealt such that the
 // sub-partitions get the same number of DMMAs: with 13 row blocks (100 neurons) warps 0..11 own one
@@ -103,7 +133,7 @@ template <int KSREG, bool STREAM>
 __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, double* Y, int P, int nCols, int kAct,
                                         const unsigned short* colPos, bool addBias, bool inplace,
                                         int warp, int lane, int nWarps,
-                                        double (&a)[KSREG]) {
+                                        double (&a)[KSREG], const double* Astage = nullptr) {
     constexpr int NB = DZ_NB;                   // column blocks (8 columns each) per group
     const int RB = L.rblocks, KS = L.ksteps;
     const int ksEff = min(KS, (kAct + 3) >> 2);    // rows >= kAct of every column are zero: their k-steps are skipped
@@ -167,8 +197,10 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
                         for (int j = 0; j < NB; j++) if (j == jj) { d[j][0] = e0; d[j][1] = e1; }
                     }
                 } else if (STREAM) {
-                    for (int k = 0; k < ksEff; k++) {   // wide-K layers: stream the A fragments
-                        double av = __ldg(Af + k * 32);
+                    // wide-K layers: the A fragments come from the TMA-staged image in shared memory (or, when it does not fit, from L2)
+                    const double* As = Astage ? Astage + (size_t)(active ? rb : 0) * KS * 32 + lane : nullptr;
+                    for (int k = 0; k < ksEff; k++) {
+                        double av = As ? As[k * 32] : __ldg(Af + k * 32);
 #pragma unroll
                         for (int j = 0; j < NB; j++) {
                             if (j < nbAct && ((blkMask >> j) & 1u)) {
@@ -211,32 +243,6 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
             }
         }
     }
-}
-
-// The bounds of a neuron are c -/+ rad with rad = sum_j |g_j|.  The sum is DEFINED chunk-wise: the generators in chunks of
-// dz_chunk(p) consecutive columns (a function of the cell's generator count alone), each chunk summed sequentially in
-// ascending order, the chunk sums added up in ascending order.  Cells of up to 128 generators -- every cell of the
-// reference's own problem sizes -- have chunks of 32; there are never more than DZ_WCH chunks.  Wide cells (hundreds of
-// generators when most neurons are unstable) can then be summed by several threads per neuron without the result depending
-// on how the work was dealt (tile size, shard, pass, kernel instantiation).
-#define DZ_WCH 4           // chunks per row at most: scratch of the wide relaxation, DZ_WCH doubles per (cell, row)
-#define DZ_WIDE_MIN 64     // tiles whose widest cell has fewer columns keep one thread per neuron
-__device__ __forceinline__ int dz_chunk(int p) {      // 32, 64, 128, ... : the smallest such that 4 chunks cover p generators
-    int ch = 32;
-    while (ch * DZ_WCH < p) ch <<= 1;
-    return ch;
-}
-// sum of |y[j P]| for j in [j0, j1), ascending, 8 loads in flight
-__device__ __forceinline__ double dz_abs_sum(const double* y, int P, int j0, int j1) {
-    double r = 0.0;
-    for (int j = j0; j < j1; j += 8) {
-        double t[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) t[q] = j + q < j1 ? y[(j + q) * P] : 0.0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) r += fabs(t[q]);       // + 0.0 beyond j1: exact
-    }
-    return r;
 }
 
 __device__ __forceinline__ double dz_sigm(double x) { return 1.0 / (1.0 + exp(-x)); }
@@ -351,10 +357,8 @@ __device__ __forceinline__ bool dz_rule(int act, double c, double lo, double hi,
 // FULL = false: the lean instantiation for ReLU / Id networks whose layers all keep their W fragments in registers -- no
 // sigmoid / tanh code and no streamed (K > 4 KSREG) products.  The kernel is sensitive to its own size (registers live
 // across the relaxation, instruction fetch): the lean variant is 5 % faster on the same work.
-// WIDE = true: tiles of few, wide cells relax with several threads per neuron (chosen by the host when the pilot run saw wide cells,
-// and for the retry / global-store passes); same results as WIDE = false bit for bit (dz_chunk).
-template <int KSREG, bool GLOBAL, bool STATS, bool FULL, bool WIDE>
-__global__ void __launch_bounds__(DZ_THREADS, 1)
+template <int KSREG, bool GLOBAL, bool STATS, bool FULL>
+__global__ void __launch_bounds__(DZ_THREADS, DZ_CTAS)
 deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, DevCallState* st, DeepzSched sp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeepzSmem& S = *reinterpret_cast<DeepzSmem*>(smem_raw);
@@ -362,7 +366,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                            : reinterpret_cast<double*>(smem_raw + sp.store_off);
     // rows whose relaxation appended a generator, [pending | being written] x cell x word, and the position table
     // (column of the current layout -> column of the next one; 0x8000: centre, 0xFFFF: unused), sized by the host
-    unsigned* const maskBase = reinterpret_cast<unsigned*>(smem_raw + dz_meta_bytes(STATS));
+    unsigned* const maskBase = reinterpret_cast<unsigned*>(smem_raw + dz_meta_bytes(STATS) + (FULL ? sp.astage_bytes : 0));
     const int mS = sp.mask_stride, mWords = sp.mask_words, maskHalf = sp.tile_max * sp.mask_stride;
     unsigned short* const colPosT = reinterpret_cast<unsigned short*>(maskBase + 2 * maskHalf);
     const int tid = threadIdx.x, NT = DZ_THREADS;
@@ -382,6 +386,9 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
 
     // ---- one-time setup: layer descriptors to smem, accumulators, the first tile ------------------
     for (int i = tid; i < L * (int)(sizeof(DevLayer) / sizeof(int)); i += NT) ((int*)S.layers)[i] = ((const int*)net->layer)[i];
+    double* const astage = (FULL && sp.astage_bytes > 0) ? reinterpret_cast<double*>(smem_raw + sp.astage_off) : nullptr;
+    unsigned aphase = 0;                          // parity of the staging barrier (every thread keeps its own copy)
+    if (FULL && astage && tid == 0) dz_mbar_init(&S.abar);
     if (tid < CLR_MAX_LAYERS) { S.sPin[tid] = 0; S.sUnst[tid] = 0; }
     if (tid < CLR_HULL_MAX) { S.hlo[tid] = INFINITY; S.hhi[tid] = -INFINITY; }
     const unsigned long long total_units =
@@ -447,13 +454,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         if (!S.more) break;
         int nCells = S.nCells;
         // store geometry of this tile: [columns ... | staging (nCells x stageW)]
-        // tiles of few, wide cells reserve DZ_WCH doubles per (cell, row) behind the staging area: the chunk sums of the
-        // relaxation with several threads per neuron (decided per tile, before any cell is deferred)
-        const int rowsMaxP = clr_pad4(net->max_rows);
-        const bool wideOk = WIDE && nCells * 2 <= NT / rowsMaxP;
-        const int scratchW = wideOk ? nCells * DZ_WCH * rowsMaxP : 0;
-        double* const wscr = store + (sp.cap - scratchW);
-        const int stageOff = sp.cap - scratchW - nCells * stageW;
+        const int stageOff = sp.cap - nCells * stageW;
         double* stage = store + stageOff;
         const int region = inplace ? stageOff : stageOff / 2;
         const int capCols = min(region / P, sp.ncol_max);
@@ -621,8 +622,17 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             const int act = Ly.act, collapse = Ly.collapse;
             const bool relax = !(act == CLR_ACT_ID && !collapse);
             const int m = Ly.m, rowsP = clr_pad4(m), mw = (m + 31) >> 5;
-            if (!(l == 0 && in.kind == 0))   // box cells enter with the first layer's product already applied
-                dz_gemm<KSREG, FULL>(Ly, cur, oth, P, nCols, S.kAct, colPosT, !relax, inplace, warp, lane, nWarps, a);
+            if (!(l == 0 && in.kind == 0)) {  // box cells enter with the first layer's product already applied
+                const double* As = nullptr;
+                if (FULL && astage && Ly.ksteps > KSREG && (unsigned)(Ly.rblocks * Ly.ksteps * 256) <= (unsigned)sp.astage_bytes) {
+                    // every warp is past the barrier that ended the previous product: the staging area is free
+                    if (tid == 0) dz_tma_load(astage, Ly.Afrag, (unsigned)(Ly.rblocks * Ly.ksteps * 256), &S.abar);
+                    dz_mbar_wait(&S.abar, aphase);
+                    aphase ^= 1u;
+                    As = astage;
+                }
+                dz_gemm<KSREG, FULL>(Ly, cur, oth, P, nCols, S.kAct, colPosT, !relax, inplace, warp, lane, nWarps, a, As);
+            }
             DZ_T(1);
             // Pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i].  In place this is safe
             // without another barrier: after the last group's barrier of the sweep every warp has read every column.
@@ -711,86 +721,29 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 unsigned rowLive = 0;                     // 1 + the highest row this thread left non-zero
                 const int G = NT / rowsP;                 // cell slots processed side by side
                 const int slot = tid / rowsP, r = tid - slot * rowsP;
-                // threads per neuron: 1, or -- few wide cells -- several, each summing whole chunks of the row
-                int tpr = 1;
-                if (WIDE && wideOk && nCells * 2 <= G) {
-                    int wmax = 0;
-                    for (int ci = 0; ci < nCells; ci++) wmax = max(wmax, (int)wCur[ci] + (int)S.uPend[flip][ci]);
-                    if (wmax >= DZ_WIDE_MIN) tpr = min(DZ_WCH, G / nCells);
-                }
-                if (!WIDE || tpr == 1) {
-                    if (slot < G && r < m) {
-                        const double bias = __ldg(Ly.bias + r);
-                        for (int ci = slot; ci < nCells; ci += G) {
-                            const int w = wCur[ci] + S.uPend[flip][ci];
-                            const int cb = colOff[ci];
-                            double* y = cur + cb * P + r;
-                            const int chm = dz_chunk(w - 1) - 1;      // chunk boundaries in front of the generators 1 + k * chunk
-                            // the row is read in groups of 8 generators, all loads of a group in flight before the (sequential)
-                            // sums; the first group stays in registers for the scaling below
-                            double v[8];
+                if (slot < G && r < m) {
+                    const double bias = __ldg(Ly.bias + r);
+                    for (int ci = slot; ci < nCells; ci += G) {
+                        const int w = wCur[ci] + S.uPend[flip][ci];
+                        const int cb = colOff[ci];
+                        double* y = cur + cb * P + r;
+                        // the row is read in groups of 8 generators, all loads of a group in flight before the sequential
+                        // (ascending, like LazySets' loops over the generators) sum; the first group stays in registers for the
+                        // scaling below.  Bounds: c -/+ rad with ONE radius sum, for one-row layers and all others alike.
+                        double v[8];
 #pragma unroll
-                            for (int q = 0; q < 8; q++) v[q] = q + 1 < w ? y[(q + 1) * P] : 0.0;
-                            const double c = y[0] + bias;
-                            double rad = 0.0, part = 0.0;
-#pragma unroll
-                            for (int q = 0; q < 8; q++) part += fabs(v[q]);       // + 0.0 beyond w: exact
-                            for (int j0 = 9; j0 < w; j0 += 8) {
-                                if (((j0 - 1) & chm) == 0) { rad += part; part = 0.0; }
-                                double t[8];
-#pragma unroll
-                                for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
-#pragma unroll
-                                for (int q = 0; q < 8; q++) part += fabs(t[q]);
-                            }
-                            rad += part;
-                            const double lo = c - rad, hi = c + rad;
-                            if (STATS && act == CLR_ACT_RELU && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
-                            double cn, la, mm;
-                            const bool unst = dz_rule<FULL>(act, c, lo, hi, cn, la, mm);
-                            if (cn != 0.0 || la != 0.0) {
-                                rowLive = r + 1;
-                                if (out.liveCount) atomicAdd(&out.liveCount[l * CLR_MAX_ROWS + r], 1);
-                            }
-                            y[0] = cn;
-                            if (collapse) y[P] = la * rad;       // LazySets' one-row linear_map: a single generator
-                            else if (la == 0.0) { for (int j = 1; j < w; j++) y[j * P] = 0.0; }     // inactive row: exactly zero, no reads
-                            else if (la != 1.0) {
-#pragma unroll
-                                for (int q = 0; q < 8; q++) if (q + 1 < w) y[(q + 1) * P] = v[q] * la;
-                                for (int j0 = 9; j0 < w; j0 += 8) {
-                                    double t[8];
-#pragma unroll
-                                    for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
-#pragma unroll
-                                    for (int q = 0; q < 8; q++) if (j0 + q < w) y[(j0 + q) * P] = t[q] * la;
-                                }
-                            }
-                            if (unst) {
-                                stage[ci * stageW + r] = mm;
-                                atomicOr(&fresh[ci * mS + (r >> 5)], 1u << (r & 31));
-                            }
-                        }
-                    }
-                } else {
-                    // ---- several threads per neuron: thread (cell, part, row) sums the chunks k = part, part + tpr, ... of its row,
-                    // the part-0 thread adds the chunk sums up in ascending order and applies the rule, all of them scale ----
-                    const int ci = slot / tpr, part = slot - ci * tpr;
-                    const bool on = slot < nCells * tpr && r < m;
-                    int w = 0, CH = 32, nCh = 1;
-                    double* y = cur;
-                    double* const myScr = wscr + (ci * DZ_WCH) * rowsMaxP + r;      // [chunk] stride rowsMaxP; slot 0: the slope
-                    if (on) {
-                        w = wCur[ci] + S.uPend[flip][ci];
-                        y = cur + colOff[ci] * P + r;
-                        CH = dz_chunk(w - 1); nCh = max(1, (w - 1 + CH - 1) / CH);
-                        for (int k = part; k < nCh; k += tpr) myScr[k * rowsMaxP] = dz_abs_sum(y, P, 1 + k * CH, min(w, 1 + (k + 1) * CH));
-                    }
-                    __syncthreads();
-                    if (on && part == 0) {
-                        const double c = y[0] + __ldg(Ly.bias + r);
+                        for (int q = 0; q < 8; q++) v[q] = q + 1 < w ? y[(q + 1) * P] : 0.0;
+                        const double c = y[0] + bias;
                         double rad = 0.0;
-                        for (int k = 0; k < nCh; k++) rad += myScr[k * rowsMaxP];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) rad += fabs(v[q]);       // + 0.0 beyond w: exact
+                        for (int j0 = 9; j0 < w; j0 += 8) {
+                            double t[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
+#pragma unroll
+                            for (int q = 0; q < 8; q++) rad += fabs(t[q]);
+                        }
                         const double lo = c - rad, hi = c + rad;
                         if (STATS && act == CLR_ACT_RELU && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
                         double cn, la, mm;
@@ -800,30 +753,22 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                             if (out.liveCount) atomicAdd(&out.liveCount[l * CLR_MAX_ROWS + r], 1);
                         }
                         y[0] = cn;
-                        if (collapse) y[P] = la * rad;
-                        myScr[0] = la;
+                        if (collapse) y[P] = la * rad;       // LazySets' one-row linear_map: a single generator
+                        else if (la == 0.0) { for (int j = 1; j < w; j++) y[j * P] = 0.0; }     // inactive row: exactly zero, no reads
+                        else if (la != 1.0) {
+#pragma unroll
+                            for (int q = 0; q < 8; q++) if (q + 1 < w) y[(q + 1) * P] = v[q] * la;
+                            for (int j0 = 9; j0 < w; j0 += 8) {
+                                double t[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
+#pragma unroll
+                                for (int q = 0; q < 8; q++) if (j0 + q < w) y[(j0 + q) * P] = t[q] * la;
+                            }
+                        }
                         if (unst) {
                             stage[ci * stageW + r] = mm;
                             atomicOr(&fresh[ci * mS + (r >> 5)], 1u << (r & 31));
-                        }
-                    }
-                    __syncthreads();
-                    if (on && !collapse) {
-                        const double la = myScr[0];
-                        if (la != 1.0) {
-                            for (int k = part; k < nCh; k += tpr) {
-                                const int j0 = 1 + k * CH, j1 = min(w, 1 + (k + 1) * CH);
-                                if (la == 0.0) { for (int j = j0; j < j1; j++) y[j * P] = 0.0; }
-                                else {
-                                    for (int j = j0; j < j1; j += 8) {
-                                        double t[8];
-#pragma unroll
-                                        for (int q = 0; q < 8; q++) t[q] = j + q < j1 ? y[(j + q) * P] : 0.0;
-#pragma unroll
-                                        for (int q = 0; q < 8; q++) if (j + q < j1) y[(j + q) * P] = t[q] * la;
-                                    }
-                                }
-                            }
                         }
                     }
                 }
@@ -1093,7 +1038,6 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
         }
         DZ_T(5);
-        if (out.liveCount && tid == 0) atomicMax(&st->max_p_out, (int)S.peakCols);      // pilot runs: columns per cell at the widest layer
         // ---- adapt the tile size to the growth just seen ---------------------------------------------------------------
         if (tid == 0) {
             if (sp.tile_cells <= 0 && sp.pass != 2) {
@@ -1101,8 +1045,6 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 // columns and staging both scale with the number of cells
                 const float perCell = S.peakNeed * margin * (float)P * (inplace ? 1.f : 2.f) + (float)stageW;
                 int T = (int)((float)(sp.cap - 16 * P) / perCell);
-                if (sp.wide && T * 2 <= NT / clr_pad4(net->max_rows))       // such a tile also carries the wide relaxation's scratch
-                    T = (int)((float)(sp.cap - 16 * P) / (perCell + (float)(DZ_WCH * clr_pad4(net->max_rows))));
                 if (sp.grow_cols > 0 && sp.pass == 0) {
                     // sigmoid / tanh layers: the growth of a cell is known, not estimated -- the largest tile whose columns,
                     // 8 columns of slack and staging fit exactly (wide cells: one more cell per tile is a large step)

@@ -47,8 +47,9 @@ struct DeepzSched {
     int tile_max;             // cells a tile may hold (<= CLR_TILE_CELLS_MAX)
     int ncol_max;             // columns a tile may hold (<= CLR_NCOL_MAX); the position table has ncol_max + 32 entries
     int store_off;            // byte offset of the column store in dynamic shared memory
+    int astage_off;           // byte offset / size of the TMA staging area of wide-K W fragments (0 bytes: none)
+    int astage_bytes;
     int fuse_tail;            // 1: the last layer (Id, at most 4 inputs and rows) is applied column by column in the output stage
-    int wide;                 // 1: tiles of few wide cells relax with several threads per neuron (scratch behind the staging area)
     long long* retry_list;
     long long* big_list;
     double* workspace;        // pass 2: gridDim.x * cap doubles
@@ -62,6 +63,7 @@ struct DeepzSmem {
     int kAct;                                 // rows of the store that can be non-zero: the next product's K (inactive
                                               // neurons at the end of a layer are skipped, see dz_gemm)
     int sMaxP;
+    unsigned long long abar;                   // mbarrier of the TMA staging of wide-K W fragments
     long long firstIdx;
     float peakNeed;
     float peakCols;                           // columns per cell at the widest layer of the tile, without the slack
@@ -91,4 +93,9 @@ __host__ __device__ inline size_t dz_meta_bytes(bool stats) {
 #ifndef DZ_MARGIN
 #define DZ_MARGIN 1.0625f   // head-room of the adaptive tile size over the growth seen so far (main pass)
 #endif
-#define DZ_THREADS 512   // 16 warps, always (4 per SM sub-partition: 128 registers per thread)
+#ifndef DZ_THREADS
+#define DZ_THREADS 512   // 16 warps (4 per SM sub-partition: 128 registers per thread)
+#endif
+#ifndef DZ_CTAS
+#define DZ_CTAS 1        // CTAs per SM (experiments: 2 x 256 threads)
+#endif

@@ -17,8 +17,10 @@
 //      other over [-1, 1]) and summed with the remainder in outward-rounded interval arithmetic; the midpoint of that
 //      interval moves the centre, its radius becomes a generator r_v e_v;
 //   4. project: the rows `vars` of the centre and of [G_lin | diag(r)]; zero columns dropped when requested.
-// Not restated: LazySets' remove_redundant_generators (merging of parallel columns) -- the zonotope returned here is
-// the same SET with the unmerged columns, see DESIGN.md.
+//   3b. (merge != 0) LazySets' remove_redundant_generators, the default of that overapproximate: on the FULL n-dimensional
+//      zonotope zero columns are dropped and every column that is a multiple of an earlier (accumulated) column is added to
+//      it -- ReachabilityBase ismultiple with its approximate comparisons.  All n components are then evaluated, not only
+//      the kept ones: whether two columns are parallel is decided in n dimensions, before the projection.
 //
 // One warp per (reach-set, kept variable): lanes over the monomials, coalesced reads of the coefficient block.
 // HBM-bound streaming kernel: 8 M (order_t + 1) bytes read per (reach-set, kept variable), a few hundred written.
@@ -29,6 +31,8 @@ struct ProjArgs {
     long long N;
     int n, KT, M, nkeep;        // space variables, time coefficients (order_t + 1), monomials, kept variables
     int remove_zero;
+    int merge;                  // 1: remove_redundant_generators before the projection (evaluates all n components: nkeep == n in phase 1)
+    int nproj; const int* pvars; // merge: the projection applied by the pack kernel (nproj kept variables)
     const int* cls;             // per monomial: -1 constant, j >= 0 linear in variable j, -2 nonlinear all-even, -3 nonlinear
     const double* coeffs;       // [N][n][KT][M]   (monomial index fastest)
     const double* rem;          // [N][n][2]       lo, hi of the remainder
@@ -135,4 +139,66 @@ __global__ void project_pack_kernel(ProjArgs A) {
     A.outN[cell] = p;
     for (int j = p; j < cap; j++)
         for (int kv = 0; kv < nk; kv++) G[(size_t)j * nk + kv] = 0.0;
+}
+
+// ---- merge != 0: phase 2 with LazySets' remove_redundant_generators on the full zonotope, then the projection ----------
+__device__ __forceinline__ bool pj_zero(double x) { return fabs(x) <= CLR_ZTOL; }
+__device__ __forceinline__ bool pj_approx(double x, double y) {
+    if (pj_zero(x) && pj_zero(y)) return true;
+    return x == y || fabs(x - y) <= CLR_RTOL * fmax(fabs(x), fabs(y));
+}
+#define PJ_NMAX 64
+// one thread per reach-set; scratch holds all n components: sc[v][0..n-1] linear, sc[v][n] centre, sc[v][n+1] radius
+__global__ void project_pack_merge_kernel(ProjArgs A) {
+    const long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (cell >= A.N) return;
+    const int n = A.n, nk = A.nproj, cap = 2 * n;
+    const double* sc = A.scratch + (size_t)cell * n * (n + 2);
+    auto entry = [&](int col, int v) -> double {          // column `col` of [G_lin | diag(r)], row v
+        return col < n ? sc[(size_t)v * (n + 2) + col] : (col - n == v ? sc[(size_t)v * (n + 2) + n + 1] : 0.0);
+    };
+    double* G = A.outG + (size_t)cell * cap * nk;
+    unsigned long long done[2] = {0ull, 0ull};            // dropped columns (zero, or merged into an earlier one)
+    int p_all = 0;
+    for (int j = 0; j < cap; j++) {                       // remove_zero_columns
+        bool any = false;
+        for (int v = 0; v < n; v++) any = any || entry(j, v) != 0.0;
+        if (!any) done[j >> 6] |= 1ull << (j & 63); else p_all++;
+    }
+    double g1[PJ_NMAX];
+    int p = 0;
+    for (int j1 = 0; j1 < cap; j1++) {
+        if ((done[j1 >> 6] >> (j1 & 63)) & 1ull) continue;
+        for (int v = 0; v < n; v++) g1[v] = entry(j1, v);
+        if (p_all > 1) {
+            for (int j2 = j1 + 1; j2 < cap; j2++) {
+                if ((done[j2 >> 6] >> (j2 & 63)) & 1ull) continue;
+                // ReachabilityBase.Arrays.ismultiple(g1, column j2)
+                bool ok = true, nofac = true; double fac = 0.0;
+                for (int v = 0; v < n && ok; v++) {
+                    const double u = g1[v], w = entry(j2, v);
+                    if (pj_zero(u)) { if (!pj_zero(w)) ok = false; continue; }
+                    if (pj_zero(w)) { ok = false; continue; }
+                    if (nofac) { nofac = false; fac = u / w; }
+                    else if (!pj_approx(fac, u / w)) ok = false;
+                }
+                if (ok) {
+                    if (!nofac && fac > 0.0) { for (int v = 0; v < n; v++) g1[v] += entry(j2, v); }
+                    else { for (int v = 0; v < n; v++) g1[v] -= entry(j2, v); }
+                    done[j2 >> 6] |= 1ull << (j2 & 63);
+                }
+            }
+        }
+        // project(Z, vars) + remove_zero_generators of the projection
+        bool any = false;
+        for (int k = 0; k < nk; k++) any = any || g1[A.pvars[k]] != 0.0;
+        if (any || !A.remove_zero) {
+            for (int k = 0; k < nk; k++) G[(size_t)p * nk + k] = g1[A.pvars[k]];
+            p++;
+        }
+    }
+    for (int k = 0; k < nk; k++) A.outC[cell * nk + k] = sc[(size_t)A.pvars[k] * (n + 2) + n];
+    A.outN[cell] = p;
+    for (int j = p; j < cap; j++)
+        for (int k = 0; k < nk; k++) G[(size_t)j * nk + k] = 0.0;
 }

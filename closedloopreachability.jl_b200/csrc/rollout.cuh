@@ -669,7 +669,9 @@ __device__ __forceinline__ void ro_mlp_small_blocked(const PointNet& net, const 
 // Narrow-network rollouts: a thread owns RO_R trajectories.  Per period the controller is evaluated for all of
 // them at once (register blocked), then each one is integrated in turn; states and controls live in
 // thread-private shared-memory slots in between, so the ODE code exists once.
+#ifndef RO_R
 #define RO_R 4
+#endif
 #ifndef RO_MINBLK
 #define RO_MINBLK 4
 #endif

@@ -17,6 +17,7 @@ PLANTS = {"Unicycle": 1, "TORA": 2, "ACC": 3, "InvertedPendulum": 4}
 PLANT_DIMS = {1: (4, 1, 2), 2: (4, 0, 1), 3: (6, 0, 1), 4: (2, 0, 1)}   # n_state, n_dist, n_ctrl
 FLAG_DEVICE_IO = 1
 FLAG_NO_STATS = 2
+FLAG_MERGE_REDUNDANT = 4
 ERR_ARG, ERR_CAPACITY, ERR_DIM, ERR_CUDA, ERR_ALLOC, ERR_STATE = -1, -2, -3, -4, -5, -6
 
 
@@ -343,7 +344,7 @@ class Context:
             self._check(self.L.clr_deepz_fetch_reduced(self.h, int(order), _ptr(c), _ptr(G), 0))
         return {"c": c, "G": G}
 
-    def project_oa(self, exps, coeffs, rem, dt, vars_keep, remove_zero_generators=True):
+    def project_oa(self, exps, coeffs, rem, dt, vars_keep, remove_zero_generators=True, remove_redundant_generators=False):
         """Batched ``_project_oa(R::AbstractTaylorModelReachSet, vars, t)`` (reference src/setops.jl:9-12) for the N reach-sets
         that end the chains of a control period (src/solve.jl:181-184).
 
@@ -363,16 +364,44 @@ class Context:
         vk = np.ascontiguousarray(vars_keep, dtype=np.int32)
         c = np.zeros((N, len(vk))); G = np.zeros((N, 2 * n, len(vk))); nc = np.zeros(N, dtype=np.int32)
         self._check(self.L.clr_project_oa(self.h, n, KT - 1, M, _ptr(exps), N, _ptr(coeffs), _ptr(rem), _ptr(dt), _ptr(vk),
-                                          len(vk), int(bool(remove_zero_generators)), _ptr(c), _ptr(G), _ptr(nc), 0))
+                                          len(vk), int(bool(remove_zero_generators)), _ptr(c), _ptr(G), _ptr(nc),
+                                          FLAG_MERGE_REDUNDANT if remove_redundant_generators else 0))
         return {"c": c, "G": G, "ncols": nc}
 
-    def project_oa_dev(self, n, order_t, exps, N, d_coeffs, d_rem, d_dt, vars_keep, remove_zero_generators, d_c, d_G, d_ncols):
+    def project_oa_dev(self, n, order_t, exps, N, d_coeffs, d_rem, d_dt, vars_keep, remove_zero_generators, d_c, d_G, d_ncols,
+                       remove_redundant_generators=False):
         """Same with device-resident arrays (CLR_FLAG_DEVICE_IO); exps / vars_keep stay host arrays."""
         exps = np.ascontiguousarray(exps, dtype=np.int32)
         vk = np.ascontiguousarray(vars_keep, dtype=np.int32)
         self._check(self.L.clr_project_oa(self.h, int(n), int(order_t), exps.shape[0], _ptr(exps), int(N), _ptr(d_coeffs), _ptr(d_rem),
                                           _ptr(d_dt), _ptr(vk), len(vk), int(bool(remove_zero_generators)), _ptr(d_c), _ptr(d_G),
-                                          _ptr(d_ncols), FLAG_DEVICE_IO))
+                                          _ptr(d_ncols), FLAG_DEVICE_IO | (FLAG_MERGE_REDUNDANT if remove_redundant_generators else 0)))
+
+    def split_zonotopes(self, Cc, G, ncols, gens, nparts):
+        """apply(ZonotopeSplitter(gens, nparts), Z) for a batch in the padded layout: Cc (N, n), G (N, cap, n), ncols (N,); gens
+        0-based.  Returns the children (N * 2^H of them, child-major) in the same layout (clr_split_zonotopes)."""
+        Cc = np.ascontiguousarray(Cc, dtype=np.float64)
+        G = np.ascontiguousarray(G, dtype=np.float64)
+        N, n = Cc.shape
+        cap = G.shape[1] if G.ndim == 3 else 0
+        nc = np.ascontiguousarray(ncols, dtype=np.int32)
+        g = np.ascontiguousarray(gens, dtype=np.int32)
+        t = np.ascontiguousarray(nparts, dtype=np.int32)
+        H = int(t.sum())
+        oc = np.empty((N << H, n)); oG = np.empty((N << H, cap, n)); on = np.empty(N << H, dtype=np.int32)
+        self._check(self.L.clr_split_zonotopes(self.h, n, N, _ptr(Cc), _ptr(G), _ptr(nc), cap, len(g), _ptr(g), _ptr(t), _ptr(oc), _ptr(oG),
+                                               _ptr(on), 0))
+        return {"c": oc, "G": oG, "ncols": on}
+
+    def sign_split(self, lo, hi):
+        """apply(SignSplitter(), U) for a batch of intervals: (lo, hi, parent index) of the pieces, order kept (clr_sign_split)."""
+        lo = np.ascontiguousarray(lo, dtype=np.float64).ravel(); hi = np.ascontiguousarray(hi, dtype=np.float64).ravel()
+        N = len(lo)
+        ol = np.empty(2 * N); oh = np.empty(2 * N); op = np.empty(2 * N, dtype=np.int64)
+        cnt = C.c_int64(0)
+        self._check(self.L.clr_sign_split(self.h, N, _ptr(lo), _ptr(hi), _ptr(ol), _ptr(oh), _ptr(op), C.byref(cnt), 0))
+        k = cnt.value
+        return ol[:k], oh[:k], op[:k]
 
     def fetch_reduced_dev(self, order, d_c, d_G):
         """Same with device-resident outputs (CLR_FLAG_DEVICE_IO): d_c (N, m), d_G (N, m*order, m)."""

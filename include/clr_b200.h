@@ -68,7 +68,9 @@ enum {
                                  results are complete in stream order on clr_stream(ctx).  partition, clr_prepost and
                                  clr_stats stay host pointers.  The DeepZ calls still synchronise once internally
                                  (they read back how many cells need the large-cell pass). */
-    CLR_FLAG_NO_STATS = 2     /* skip the per-layer statistics (stats may then be NULL) */
+    CLR_FLAG_NO_STATS = 2,    /* skip the per-layer statistics (stats may then be NULL) */
+    CLR_FLAG_MERGE_REDUNDANT = 4  /* clr_project_oa: LazySets' remove_redundant_generators on the full zonotope before the projection --
+                                 the default of overapproximate(::Vector{TaylorModel1}, Zonotope), i.e. what src/setops.jl:10 runs */
 };
 
 typedef struct clr_ctx clr_ctx;
@@ -257,6 +259,19 @@ int32_t clr_rollout_plant(clr_ctx* ctx, const clr_net* net, const clr_prepost* p
                           double abstol, double reltol, int32_t substeps, int32_t pow_mode, double* X_end, double* U,
                           int32_t* naccept, int32_t* nreject, int32_t log_cap, int32_t* log_n, double* log_t,
                           double* log_u, int32_t flags);
+
+/* ---- the other splitters on the device (reference src/splitters.jl:30-43, :60-71) ---------------------------------
+ * clr_split_zonotopes: apply(ZonotopeSplitter(gens, nparts), Z) = LazySets split(Z, gens, nparts) for a batch of zonotopes in
+ * the padded layout (C n x N, G n x cap x N, ncols N; gens 0-based): generator gens[i] is halved nparts[i] times, each
+ * halving doubles the list ((Z - g/2, Z + g/2) in place of Z), so every input has 2^H children, H = sum(nparts), written
+ * child-major behind one another in the same padded layout (ready for clr_deepz_zonotopes_padded).
+ * clr_sign_split: apply(SignSplitter(), U) for N control intervals: an interval with 0 in its interior becomes [lo, 0] and
+ * [0, hi]; out_lo / out_hi / out_parent need room for 2 N entries, *out_count receives the number written (order kept). */
+int32_t clr_split_zonotopes(clr_ctx* ctx, int32_t n, int64_t N, const double* C, const double* G, const int32_t* ncols, int32_t cap,
+                            int32_t n_gens, const int32_t* gens, const int32_t* nparts, double* out_C, double* out_G,
+                            int32_t* out_ncols, int32_t flags);
+int32_t clr_sign_split(clr_ctx* ctx, int64_t N, const double* lo, const double* hi, double* out_lo, double* out_hi,
+                       int64_t* out_parent, int64_t* out_count, int32_t flags);
 
 /* ---- several GPUs of one box behind one handle --------------------------------------------------
  * Replaces, for a caller with more than one device, the same reference loops as clr_deepz_boxgrid / clr_rollout

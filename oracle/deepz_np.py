@@ -486,7 +486,8 @@ def reduce_order_gir05(c, G, r=2):
 # overapproximate(::Vector{<:TaylorModelN}, Zonotope): constant + linear terms -> centre / generators, the nonlinear
 # terms and the remainder -> an interval whose midpoint moves the centre and whose radius is a generator r_v e_v.
 # Interval additions round outwards exactly (directed rounding via TwoSum); multiplications by 0 / +-1 are exact.
-# LazySets' remove_redundant_generators (merging parallel columns) is not restated: same set, unmerged columns.
+# LazySets' overapproximate(::Vector{TaylorModel1}, Zonotope; remove_redundant_generators=true) then merges parallel
+# generators (remove_redundant_generators below) before the projection.
 # --------------------------------------------------------------------------------------
 def _two_sum(a: float, b: float):
     s = a + b
@@ -519,7 +520,51 @@ def monomial_table(n: int, order: int):
     return np.array(out, dtype=np.int32)
 
 
-def project_oa_taylor_model(exps, coeffs, rem, dt, vars_keep, remove_zero_generators=True):
+def ismultiple(u, v):
+    """ReachabilityBase.Arrays.ismultiple(u, v) [UPSTREAM-RECALL]: (True, factor) if u = factor * v entry by entry (entries
+    compared with isapproxzero / _isapprox), (True, 0) if both are zero, else (False, 0)."""
+    no_factor, factor = True, 0.0
+    for ui, vi in zip(u, v):
+        if isapproxzero(ui):
+            if not isapproxzero(vi):
+                return False, 0.0
+            continue
+        if isapproxzero(vi):
+            return False, 0.0
+        if no_factor:
+            no_factor, factor = False, ui / vi
+        elif not _isapprox(factor, ui / vi):
+            return False, 0.0
+    return True, (0.0 if no_factor else factor)
+
+
+def remove_redundant_generators(G):
+    """LazySets.remove_redundant_generators(Z) on the generator matrix [UPSTREAM-RECALL]: zero columns are dropped; then, column
+    by column, every later column that is a multiple of the (already accumulated) column is added to it (subtracted when the
+    factor is negative) and dropped."""
+    G = np.asarray(G, dtype=np.float64)
+    if G.shape[1] <= 1:
+        return G
+    G = remove_zero_columns(G)
+    p = G.shape[1]
+    done = [False] * p
+    cols = []
+    for j1 in range(p):
+        if done[j1]:
+            continue
+        g1 = G[:, j1].copy()
+        for j2 in range(j1 + 1, p):
+            if done[j2]:
+                continue
+            ok, f = ismultiple(g1, G[:, j2])
+            if ok:
+                g1 = g1 + G[:, j2] if f > 0.0 else g1 - G[:, j2]
+                done[j2] = True
+        cols.append(g1)
+    return np.stack(cols, axis=1) if cols else np.zeros((G.shape[0], 0))
+
+
+def project_oa_taylor_model(exps, coeffs, rem, dt, vars_keep, remove_zero_generators=True, remove_redundant=False):
     """One reach-set.  exps (M, n); coeffs (n, KT, M); rem (n, 2); dt scalar; vars_keep 0-based.
     Returns (c (n_keep,), G (n_keep, p))."""
     exps = np.asarray(exps); n = exps.shape[1]
@@ -549,6 +594,8 @@ def project_oa_taylor_model(exps, coeffs, rem, dt, vars_keep, remove_zero_genera
         c[v] = c0m + 0.5 * (lo + hi)
         rad[v] = 0.5 * _add_up(hi, -lo)
     G = np.hstack([Glin, np.diag(rad)])
+    if remove_redundant:                                             # default of LazySets' overapproximate: on the FULL zonotope
+        G = remove_redundant_generators(G)
     vk = list(vars_keep)
     c, G = c[vk], G[vk, :]                                           # LazySets.project
     if remove_zero_generators:

@@ -80,6 +80,27 @@ int main(void) {
     const int32_t bad[4] = {4, 0, 3, 5};
     rc = clr_deepz_boxgrid(ctx, net, 4, bad, centers, radii, 0, 1, &pp, out_lo, out_hi, NULL, NULL, NULL, 0, CLR_FLAG_NO_STATS);
     if (rc != CLR_ERR_ARG || !clr_last_error(ctx)[0]) { fprintf(stderr, "bad partition not rejected (%d)\n", rc); return 1; }
+    /* (4) two shards behind one handle, without Python / torch / NCCL (clr_create_multi; device 0 twice on a one-GPU box): the
+       boxes in cell order and the peer-gathered hull equal the single-context run bit for bit */
+    {
+        const int32_t devs[2] = {0, 0};
+        clr_multi* mc = NULL; clr_multi_net* mn = NULL;
+        if (clr_create_multi(devs, 2, &mc) != 0) { fprintf(stderr, "clr_create_multi: %s\n", clr_last_error(NULL)); return 1; }
+        if (clr_multi_size(mc) != 2 || !clr_multi_ctx(mc, 1)) { fprintf(stderr, "multi handle malformed\n"); return 1; }
+        if (clr_multi_net_upload(mc, 3, dims, act, (const double* const*)W, (const double* const*)b, &mn) != 0) {
+            fprintf(stderr, "clr_multi_net_upload: %s\n", clr_multi_last_error(mc)); return 1;
+        }
+        double m_lo[240], m_hi[240], mh_lo, mh_hi, ms[2]; int64_t bounds[3];
+        for (int mode = 0; mode < 3; mode += 2) {       /* contiguous and block-cyclic shards */
+            if (clr_multi_deepz_boxgrid(mc, mn, 4, part, centers, radii, 0, N, &pp, m_lo, m_hi, &mh_lo, &mh_hi, &st, mode, bounds, ms) != 0) {
+                fprintf(stderr, "clr_multi_deepz_boxgrid: %s\n", clr_multi_last_error(mc)); return 1;
+            }
+            if (memcmp(m_lo, out_lo, sizeof out_lo) || memcmp(m_hi, out_hi, sizeof out_hi) || mh_lo != hull_lo || mh_hi != hull_hi ||
+                st.n_cells != N || bounds[0] != 0 || bounds[2] != N) { fprintf(stderr, "two shards differ from one context (mode %d)\n", mode); return 1; }
+        }
+        clr_multi_net_free(mn);
+        clr_destroy_multi(mc);
+    }
     printf("abi_check ok: 240 cells, hull [%.6f, %.6f], %lld launches\n", hull_lo, hull_hi, (long long)clr_launch_count(ctx));
     clr_net_free(net);
     clr_destroy(ctx);

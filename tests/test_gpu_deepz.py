@@ -563,6 +563,41 @@ def test_project_oa_batched(ctx):
         ctx.deepz_zonotopes_padded(dn, big["c"][:2], big["G"][:2], np.array([99, 0], dtype=np.int32))   # ncols > cap
 
 
+def test_project_oa_merges_redundant_generators(ctx):
+    """CLR_FLAG_MERGE_REDUNDANT: LazySets' remove_redundant_generators on the full zonotope before the projection (what
+    src/setops.jl:10 runs by default), against the NumPy restatement -- Taylor models shaped like TMJets output for a controlled
+    plant: the input variables enter their own component only, so their linear and remainder generators are parallel."""
+    from oracle import deepz_np as dz
+    from test_oracle import _random_taylor_models
+    rng = np.random.default_rng(33)
+    N, n = 300, 6
+    exps, coeffs, rem, dt = _random_taylor_models(rng, N, n, 4, 2)
+    deg = exps.sum(axis=1)
+    lin = [int(np.flatnonzero((deg == 1) & (exps[:, j] == 1))[0]) for j in range(n)]
+    for v in (4, 5):                                   # components 4, 5: u' = 0 -> u(t) = c + s xi_v exactly
+        coeffs[:, v, :, :] = 0.0
+        coeffs[:, v, 0, 0] = rng.normal(size=N)
+        coeffs[:, v, 0, lin[v]] = 0.05
+        coeffs[:, :4, :, lin[v]] *= (rng.random((N, 1, 1)) > 0.5)      # in half of the sets the states do not depend on xi_v at all
+    coeffs[::7, 1, :, :] = 0.0; rem[::7, 1, :] = 0.0                   # a component that is identically zero now and then
+    for vk in ([0, 1, 2, 3], [0, 4], list(range(n))):
+        got = ctx.project_oa(exps, coeffs, rem, dt, vk, remove_redundant_generators=True)
+        merged = 0
+        for i in range(N):
+            c, G = dz.project_oa_taylor_model(exps, coeffs[i], rem[i], dt[i], vk, remove_redundant=True)
+            _, G0 = dz.project_oa_taylor_model(exps, coeffs[i], rem[i], dt[i], vk, remove_redundant=False)
+            merged += G.shape[1] < G0.shape[1]
+            p = got["ncols"][i]
+            assert p == G.shape[1], (vk, i, p, G.shape)
+            scale = max(np.abs(G).max() if G.size else 0.0, np.abs(c).max(), 1e-300)
+            np.testing.assert_allclose(got["c"][i], c, rtol=0, atol=1e-12 * scale)
+            np.testing.assert_allclose(got["G"][i, :p].T, G, rtol=0, atol=1e-12 * scale)          # signed, column order included
+            assert not got["G"][i, p:].any()
+        assert merged > 0 or vk == [0, 1, 2, 3]
+    plain = ctx.project_oa(exps, coeffs, rem, dt, [0, 4])
+    assert np.all(plain["ncols"] >= ctx.project_oa(exps, coeffs, rem, dt, [0, 4], remove_redundant_generators=True)["ncols"])
+
+
 def test_setops_golden_fixture_on_the_device(ctx):
     """clr_project_oa against the committed fixture (tests/golden/setops_oracle.npz)."""
     z = np.load(os.path.join(GOLDEN, "setops_oracle.npz"))
@@ -598,3 +633,55 @@ def test_cells_too_large_for_shared_memory_take_the_global_store_pass(ctx):
     assert got["hull_lo"][0] == got["lo"].min() and got["hull_hi"][0] == got["hi"].max()
     kept = ctx.deepz_zonotopes(dn, C, off, G, post=("shift", -10.0), keep_cap=1024)
     assert np.array_equal(kept["lo"], got["lo"]) and np.array_equal(kept["hi"], got["hi"])
+
+
+def test_device_side_zonotope_and_sign_splitters(ctx):
+    """clr_split_zonotopes / clr_sign_split (src/splitters.jl:30-43, :60-71) against the host mirror (clr_b200/splitters.py, itself
+    the restatement of LazySets split(Z, gens, nparts)): children bit for bit and in the same order; chained into the
+    controller propagation."""
+    import clr_b200
+    rng = np.random.default_rng(17)
+    N, n, cap = 37, 4, 9
+    ncols = rng.integers(5, cap + 1, N).astype(np.int32)
+    Cc = rng.uniform(-0.7, 0.7, (N, n))
+    G = np.zeros((N, cap, n))
+    for i in range(N):
+        G[i, :ncols[i]] = 0.05 * rng.uniform(-1, 1, (ncols[i], n))
+    gens, nparts = [0, 3, 4, 1], [2, 1, 0, 1]
+    got = ctx.split_zonotopes(Cc, G, ncols, gens, nparts)
+    H = sum(nparts)
+    assert got["c"].shape == (N << H, n)
+    for i in range(N):
+        ref = clr_b200.split_zonotope(Cc[i], G[i, :ncols[i]].T, gens, nparts)
+        assert len(ref) == 1 << H
+        for b in range(1 << H):
+            c, Gr = ref.cell(b)
+            k = (i << H) + b
+            assert np.array_equal(got["c"][k], c), (i, b)
+            assert got["ncols"][k] == ncols[i]
+            assert np.array_equal(got["G"][k, :ncols[i]].T, Gr), (i, b)
+            assert not got["G"][k, ncols[i]:].any()
+    # the children go straight into the controller propagation (padded layout)
+    net = load_net("TORA_ReLU")
+    dn = ctx.upload(net)
+    out = ctx.deepz_zonotopes_padded(dn, got["c"], got["G"], got["ncols"], post=("shift", -10.0))
+    off = np.concatenate([[0], np.cumsum(got["ncols"])]).astype(np.int64)
+    Gc = np.concatenate([got["G"][k, :got["ncols"][k]] for k in range(len(off) - 1)])
+    ref = _oracle().deepz_zonotopes(_oracle().Net(net.as_tuples()), got["c"], off, Gc, post=("shift", -10.0))
+    _cmp_boxes(out, ref)
+    with pytest.raises(Exception):
+        ctx.split_zonotopes(Cc, G, ncols, [8], [1])              # generator 8 does not exist in the cells with fewer columns
+    # SignSplitter on the control intervals of a split
+    lo = np.array([-1.0, 0.0, -3.0, -1.0, 0.5, -2.0, -0.0, 1e-300]); hi = np.array([2.0, 2.0, -1.0, 0.0, 0.7, 5.0, 1.0, 2e-300])
+    l2, h2, par = ctx.sign_split(lo, hi)
+    exp = []
+    for i, (a, b) in enumerate(zip(lo, hi)):
+        exp += [(x, y, i) for x, y in clr_b200.SignSplitter().apply(float(a), float(b))]
+    assert [(float(a), float(b), int(p)) for a, b, p in zip(l2, h2, par)] == exp
+    big_lo = rng.uniform(-1, 0.5, 100003); big_hi = big_lo + rng.uniform(0, 1, 100003)
+    l3, h3, p3 = ctx.sign_split(big_lo, big_hi)
+    straddle = (big_lo < 0) & (big_hi > 0)
+    assert len(l3) == 100003 + straddle.sum() and np.all(np.diff(p3) >= 0)
+    assert np.array_equal(np.bincount(p3, minlength=100003), 1 + straddle.astype(np.int64))
+    first = np.concatenate([[True], np.diff(p3) > 0])
+    assert np.array_equal(l3[first], big_lo) and np.all(h3[first][straddle] == 0.0)

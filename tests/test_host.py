@@ -142,13 +142,29 @@ r = cbind.deepz_boxgrid(cbind.Net(net.as_tuples()), g.partition, g.centers, g.ra
 lo, hi = parallel.gather_hull(torch.from_numpy(r["lo"].min(0)), torch.from_numpy(r["hi"].max(0)))
 tmax = parallel.max_over_ranks(1.0 + rank)
 tot = parallel.sum_over_ranks(cnt)
+per_rank = parallel.gather_scalars(10.0 * (rank + 1))             # per-rank times of the bench line
+assert per_rank == [10.0 * (k + 1) for k in range(world)]
+# block-cyclic shards (bench default at N > 1): rank r takes the blocks r, r + world, ... of `blk` cells; the oracle has no
+# strided call, so the shard is evaluated block by block -- reassembled it must equal the contiguous result, order included
+blk = 16
+nb = (len(g) + blk - 1) // blk
+mine = []
+for j in range(rank, nb, world):
+    rr = cbind.deepz_boxgrid(cbind.Net(net.as_tuples()), g.partition, g.centers, g.radii, cell_begin=j * blk,
+                             cell_count=min(blk, len(g) - j * blk), post=("shift", -10.0))
+    mine.append((j, rr["lo"]))
+cyc = [None] * world
+dist.all_gather_object(cyc, mine)
 parts = [None] * world
 dist.all_gather_object(parts, r["lo"])
 if rank == 0:
+    blocks = sorted([b for part in cyc for b in part], key=lambda t: t[0])
+    cyc_lo = np.concatenate([b[1] for b in blocks])
     full = cbind.deepz_boxgrid(cbind.Net(net.as_tuples()), g.partition, g.centers, g.radii, post=("shift", -10.0))
     assert np.array_equal(parallel.concat_shards(parts), full["lo"])
     assert float(lo[0]) == full["lo"].min() and float(hi[0]) == full["hi"].max()
     assert tmax == float(world) and tot == len(g)
+    assert np.array_equal(cyc_lo, full["lo"])
     print("GLOO_OK")
 dist.destroy_process_group()
 '''

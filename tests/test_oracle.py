@@ -246,6 +246,41 @@ def test_project_oa_hand_example():
     assert G1.shape == (1, 4) and np.array_equal(G1[0], [0.0, 1.0, 0.0, 0.0]) and c1[0] == 2.0
 
 
+def test_remove_redundant_generators_hand_examples():
+    """LazySets.remove_redundant_generators (the default of overapproximate(::Vector{TaylorModel1}, Zonotope), which
+    _project_oa runs, src/setops.jl:10): zero columns dropped, multiples merged into the first of them."""
+    G = np.array([[1.0, 2.0, 0.0, 0.0], [0.0, 0.0, 0.0, 3.0]])
+    np.testing.assert_array_equal(dz.remove_redundant_generators(G), [[3.0, 0.0], [0.0, 3.0]])
+    G = np.array([[1.0, -2.0, 0.5], [1.0, -2.0, 0.25]])                   # negative factor: subtracted
+    np.testing.assert_array_equal(dz.remove_redundant_generators(G), [[3.0, 0.5], [3.0, 0.25]])
+    G = np.array([[1.0, 1.0, 1.0], [0.0, 1e-20, 0.0]])                    # 1e-20 is approximately zero: all three are multiples
+    np.testing.assert_array_equal(dz.remove_redundant_generators(G), [[3.0], [1e-20]])
+    assert dz.ismultiple([1.0, 2.0], [2.0, 4.0]) == (True, 0.5)
+    assert dz.ismultiple([0.0, 0.0], [0.0, 0.0]) == (True, 0.0)
+    assert dz.ismultiple([1.0, 0.0], [1.0, 1.0])[0] is False
+    # the box of the zonotope does not change, the set neither (generators parallel to each other add up)
+    rng = np.random.default_rng(0)
+    G = rng.normal(size=(4, 9)); G[:, 5] = -0.3 * G[:, 1]; G[:, 7] = 2.0 * G[:, 1]; G[:, 3] = 0.0
+    R = dz.remove_redundant_generators(G)
+    assert R.shape == (4, 6)
+    np.testing.assert_allclose(np.abs(R).sum(axis=1), np.abs(G).sum(axis=1), rtol=1e-14)
+
+
+def test_project_oa_with_redundant_generators():
+    # x(t) = 1 + xi1 + [-0.1, 0.1];  u(t) = 0.5 xi2 + [-0.2, 0.2]: each linear column is parallel to the remainder generator of
+    # its own component, so overapproximate's default merges them: G = diag(1.1, 0.7) instead of four columns
+    exps = dz.monomial_table(2, 1)
+    coeffs = np.zeros((2, 1, 3)); coeffs[0, 0] = [1.0, 1.0, 0.0]; coeffs[1, 0] = [0.0, 0.0, 0.5]
+    rem = np.array([[-0.1, 0.1], [-0.2, 0.2]])
+    c, G = dz.project_oa_taylor_model(exps, coeffs, rem, 0.0, [0, 1], remove_redundant=True)
+    np.testing.assert_allclose(G, [[1.1, 0.0], [0.0, 0.7]], rtol=0, atol=1e-15)
+    c2, G2 = dz.project_oa_taylor_model(exps, coeffs, rem, 0.0, [0, 1], remove_redundant=False)
+    assert G2.shape == (2, 4) and np.array_equal(c, c2)
+    # projection AFTER the merge: keeping only x leaves its merged generator
+    c3, G3 = dz.project_oa_taylor_model(exps, coeffs, rem, 0.0, [0], remove_redundant=True)
+    np.testing.assert_allclose(G3, [[1.1]], rtol=0, atol=1e-15)
+
+
 def test_project_oa_encloses_the_taylor_model():
     rng = np.random.default_rng(11)
     exps, coeffs, rem, dt = _random_taylor_models(rng, 5, 3, 4, 3)
