@@ -17,7 +17,7 @@ MAX_LAYERS = 32
 SYMBOLS = [
     "clr_create", "clr_destroy", "clr_last_error", "clr_stream", "clr_synchronize", "clr_launch_count",
     "clr_device_alloc", "clr_device_free", "clr_memcpy_h2d", "clr_memcpy_d2h", "clr_set_tile_cells",
-    "clr_set_profiling", "clr_last_pass_info", "clr_set_reorder", "clr_measure_fp64_peak", "clr_last_device_error",
+    "clr_set_profiling", "clr_last_pass_info", "clr_set_reorder", "clr_measure_fp64_peak", "clr_last_device_error", "clr_set_tiny",
     "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_boxgrid_cyclic", "clr_deepz_zonotopes", "clr_deepz_zonotopes_padded",
     "clr_deepz_fetch_zonotopes", "clr_deepz_fetch_reduced", "clr_project_oa", "clr_forward_points", "clr_rollout",
     "clr_plant_compile", "clr_plant_free", "clr_rollout_plant",
@@ -75,6 +75,8 @@ def lib():
     L.clr_set_tile_cells.restype = i32
     L.clr_set_reorder.argtypes = [vp, i32]
     L.clr_set_reorder.restype = i32
+    L.clr_set_tiny.argtypes = [vp, i32]
+    L.clr_set_tiny.restype = i32
     L.clr_set_profiling.argtypes = [vp, i32]
     L.clr_set_profiling.restype = i32
     L.clr_last_pass_info.argtypes = [vp, vp, vp, vp]

@@ -21,6 +21,7 @@
 #include "reduce.cuh"
 #include "project.cuh"
 #include "split.cuh"
+#include "tiny.cuh"
 
 #define CLR_BOUNCE_BYTES (1u << 20)  // pinned bounce buffer of the small-call path
 #define CLR_BOUNCE_IN_MAX (256u << 10)
@@ -118,6 +119,7 @@ struct clr_ctx {
     int* h_live = nullptr;               // pinned
     long long* d_pilot = nullptr;
     int reorder = 1;                     // clr_set_reorder
+    int tiny = 1;                        // clr_set_tiny: narrow networks take the one-warp-per-cell kernel
     // optional per-pass timing of the last DeepZ call (clr_set_profiling)
     int profiling = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -738,7 +740,21 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     sp.pass = 0;
     ctx->pass_ms[0] = ctx->pass_ms[1] = ctx->pass_ms[2] = 0.f;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
+    // Narrow networks (every layer at most 32 neurons wide: ACC, VerticalCAS, InvertedPendulum ...) without statistics or kept
+    // zonotopes take the one-small-CTA-per-cell kernel (tiny.cuh): the tiled DMMA kernel's phases are a ~40 us latency chain there.
+    bool tiny = !kstats && keep_cap == 0 && ctx->tile_cells == 0 && ctx->tiny && D.n_in <= TN_ROWS;
+    for (int l = 0; l < D.L && tiny; l++) tiny = D.layer[l].m <= TN_ROWS && D.layer[l].n <= TN_ROWS;
+    const int tiny_cols = worst_cols(D, p0max) + 1;
+    const size_t tsm = ((size_t)tiny_cols + TN_WARPS) * TN_ROWS * sizeof(double);      // the cell's store + the partial radius sums
+    tiny = tiny && tsm <= smem_total;
+    if (tiny) {
+        if (tsm > 48 * 1024) CU(cudaFuncSetAttribute(deepz_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        const long long per_sm = std::max<long long>(1, std::min<long long>(8, (long long)(smem_total / (tsm + 1024))));
+        const int tgrid = (int)std::max<long long>(1, std::min<long long>(N, (long long)ctx->sms * per_sm));
+        deepz_tiny_kernel<<<tgrid, TN_WARPS * 32, tsm, ctx->stream>>>(c->dev, in, out, ctx->d_state, tiny_cols);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    } else if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
     bool fast_done = false;
@@ -751,7 +767,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         fast_done = ctx->h_state->n_retry == 0 && ctx->h_state->n_big == 0;
     }
     if (!fast || ctx->h_state->n_retry > 0) {
-        if ((rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
+        if (!tiny && (rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         // how many cells did not fit in shared memory at all?
         CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(DevCallState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -979,6 +995,11 @@ int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells) {
 int32_t clr_set_reorder(clr_ctx* ctx, int32_t on) {
     if (!ctx) return CLR_ERR_ARG;
     ctx->reorder = on != 0;
+    return 0;
+}
+int32_t clr_set_tiny(clr_ctx* ctx, int32_t on) {
+    if (!ctx) return CLR_ERR_ARG;
+    ctx->tiny = on != 0;
     return 0;
 }
 int32_t clr_set_profiling(clr_ctx* ctx, int32_t on) {

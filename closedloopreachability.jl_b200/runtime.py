@@ -193,6 +193,9 @@ class Context:
     def set_reorder(self, on: bool):
         self._check(self.L.clr_set_reorder(self.h, 1 if on else 0))
 
+    def set_tiny(self, on: bool):
+        self._check(self.L.clr_set_tiny(self.h, 1 if on else 0))
+
     def set_profiling(self, on: bool):
         self._check(self.L.clr_set_profiling(self.h, 1 if on else 0))
 

@@ -125,6 +125,10 @@ int32_t clr_set_tile_cells(clr_ctx* ctx, int32_t cells);
    inactive neurons come last, so that the layer products skip their all-zero rows.  Results agree with the unordered
    network to ~1e-16 relative (summation order); every shard of one split uses the same order. */
 int32_t clr_set_reorder(clr_ctx* ctx, int32_t on);
+/* Narrow networks (every layer, incl. folded pre/post-processing, at most 32 neurons wide -- ACC, VerticalCAS, InvertedPendulum:
+   the reference's own CPU-runnable sizes) run a one-warp-per-cell kernel when neither statistics nor kept zonotopes are
+   requested (default on; results agree with the tiled kernel to rounding, ~1e-16 relative, not bit for bit). */
+int32_t clr_set_tiny(clr_ctx* ctx, int32_t on);
 /* on: CUDA events bracket each pass of the following DeepZ calls (main, retry, big-cell) */
 int32_t clr_set_profiling(clr_ctx* ctx, int32_t on);
 /* device time (ms) of the three passes of the last DeepZ call (needs profiling on), the number of

@@ -274,12 +274,60 @@ function rollout_logged(ctx::Context, dnet::DeviceNetwork, pp::PrePost, plant::I
     return Xend, U, ln, lt, lu
 end
 
+"""
+Block-cyclic shard of a split (`clr_deepz_boxgrid_cyclic`): local cell i is cell `cell_begin + (i ÷ block)·stride + i mod block`
+(0-based ids).  Device r of G takes `cell_begin = r·block`, `stride = G·block`.
+"""
+function controller_forward_boxes_cyclic(ctx::Context, dnet::DeviceNetwork, g::BoxGrid, pp::PrePost, m::Integer,
+                                         cell_begin::Integer, cell_count::Integer, block::Integer, stride::Integer)
+    lo = Matrix{Float64}(undef, m, cell_count); hi = similar(lo)
+    check(ctx, ccall((:clr_deepz_boxgrid_cyclic, LIB), Int32,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Int64, Ref{PrePost},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Int32, Int32),
+                     ctx.h, dnet.h, length(g.partition), g.partition, g.centers, g.radii, cell_begin, cell_count, block, stride, pp,
+                     lo, hi, C_NULL, C_NULL, C_NULL, 0, 2))
+    return lo, hi
+end
+
+"""
+`apply(ZonotopeSplitter(gens, nparts), Z)` (src/splitters.jl:30-43) for a batch in the padded layout, on the device
+(`clr_split_zonotopes`; `gens` 1-based like in Julia).  Returns the children (2^sum(nparts) per input, child-major) in the same layout.
+"""
+function split_zonotopes(ctx::Context, C::Matrix{Float64}, G::Array{Float64,3}, ncols::Vector{Int32}, gens::Vector{<:Integer},
+                         nparts::Vector{<:Integer})
+    n, N = size(C); cap = size(G, 2); H = sum(nparts)
+    oC = Matrix{Float64}(undef, n, N << H); oG = Array{Float64}(undef, n, cap, N << H); oN = Vector{Int32}(undef, N << H)
+    check(ctx, ccall((:clr_split_zonotopes, LIB), Int32,
+                     (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32, Int32, Ptr{Int32}, Ptr{Int32},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Int32),
+                     ctx.h, n, N, C, G, ncols, cap, length(gens), Int32.(gens .- 1), Int32.(nparts), oC, oG, oN, 0))
+    return oC, oG, oN
+end
+
+"`apply(SignSplitter(), U)` (src/splitters.jl:60-71) for a batch of control intervals: pieces (lo, hi) and their parent index (1-based)."
+function sign_split(ctx::Context, lo::Vector{Float64}, hi::Vector{Float64})
+    N = length(lo)
+    ol = Vector{Float64}(undef, 2N); oh = similar(ol); op = Vector{Int64}(undef, 2N); cnt = Ref{Int64}(0)
+    check(ctx, ccall((:clr_sign_split, LIB), Int32,
+                     (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ref{Int64}, Int32),
+                     ctx.h, N, lo, hi, ol, oh, op, cnt, 0))
+    k = cnt[]
+    return ol[1:k], oh[1:k], op[1:k] .+ 1
+end
+
+function last_device_error(ctx::Context)
+    code = Ref{Int32}(0)
+    check(ctx, ccall((:clr_last_device_error, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), ctx.h, code))
+    return code[]
+end
+
 # ---- tuning / diagnostics ------------------------------------------------------------------------------------------
 synchronize(ctx::Context) = check(ctx, ccall((:clr_synchronize, LIB), Int32, (Ptr{Cvoid},), ctx.h))
 stream(ctx::Context) = ccall((:clr_stream, LIB), Ptr{Cvoid}, (Ptr{Cvoid},), ctx.h)
 launch_count(ctx::Context) = ccall((:clr_launch_count, LIB), Int64, (Ptr{Cvoid},), ctx.h)
 set_tile_cells!(ctx::Context, cells::Integer) = check(ctx, ccall((:clr_set_tile_cells, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, cells))
 set_reorder!(ctx::Context, on::Bool) = check(ctx, ccall((:clr_set_reorder, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, on))
+set_tiny!(ctx::Context, on::Bool) = check(ctx, ccall((:clr_set_tiny, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, on))
 set_profiling!(ctx::Context, on::Bool) = check(ctx, ccall((:clr_set_profiling, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, on))
 function last_pass_info(ctx::Context)
     ms = zeros(3); retried = Ref{Int64}(0); big = Ref{Int64}(0)
@@ -316,6 +364,7 @@ mutable struct MultiContext
     end
 end
 Base.length(mc::MultiContext) = Int(ccall((:clr_multi_size, LIB), Int32, (Ptr{Cvoid},), mc.h))
+device_context(mc::MultiContext, i::Integer) = ccall((:clr_multi_ctx, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), mc.h, i - 1)   # raw clr_ctx* of device i
 function mcheck(mc::MultiContext, rc::Int32)
     rc == 0 && return nothing
     msg = unsafe_string(ccall((:clr_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), mc.h))

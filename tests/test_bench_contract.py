@@ -41,3 +41,9 @@ def test_gpu_arm_prints_one_json_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert d["clocks"]["sm_mhz"] is None or d["clocks"]["sm_mhz"] > 0
+    # the whole-step roofline can be recomputed from the line itself, the other regimes and the per-rank
+    # times are on the same line, and the FP64 peak was measured in this run
+    assert abs(r["frac"] - r["algorithmic_flops_per_step"] / (d["ms_per_step"] * 1e-3) / 1e12 / r["peak"]) < 1e-6 * r["frac"] + 1e-12
+    assert 20.0 < r["peak"] < 60.0 and "measured in this run" in r["peak_source"]
+    assert set(d["regimes"]) == {"mixed", "dense"} and all(v["value"] > 0 and 0 < v["roofline"]["frac"] < 1 for v in d["regimes"].values())
+    assert d["per_rank"]["ms_per_step"] == [d["ms_per_step"]] and d["per_rank"]["cells"] == [8 ** 6]

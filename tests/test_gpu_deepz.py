@@ -685,3 +685,61 @@ def test_device_side_zonotope_and_sign_splitters(ctx):
     assert np.array_equal(np.bincount(p3, minlength=100003), 1 + straddle.astype(np.int64))
     first = np.concatenate([[True], np.diff(p3) > 0])
     assert np.array_equal(l3[first], big_lo) and np.all(h3[first][straddle] == 0.0)
+
+
+def test_narrow_networks_take_the_one_cta_per_cell_kernel(ctx):
+    """Networks whose layers are all <= 32 neurons wide (ACC, VerticalCAS, InvertedPendulum: the reference's CPU-runnable sizes) run
+    deepz_tiny_kernel when no statistics / zonotopes are requested: against the oracle, against the tiled kernel (to rounding),
+    box grids and zonotope batches, pre- and post-processing, hull, and a large batch."""
+    import clr_b200
+    from clr_b200 import workloads
+    rng = np.random.default_rng(41)
+    A = np.zeros((5, 6)); A[2, 4] = 1.0; A[3, 0], A[3, 3] = 1.0, -1.0; A[4, 1], A[4, 4] = 1.0, -1.0
+    d = np.array([30.0, 1.4, 0.0, 0.0, 0.0])
+    cases = [("ACC_relu", (A, d), None, 6), ("ACC_tanh", (A, d), None, 6), ("InvertedPendulum", None, None, 2),
+             ("VerticalCAS_3", None, ("matrix", np.array([[1.0, -1.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0, 2.0]])), None)]
+    for name, pre, post, n0 in cases:
+        net = load_net(name)
+        n = n0 or net.dim_in
+        dn = ctx.upload(net)
+        on = _oracle().Net(net.as_tuples())
+        C, off, G = workloads.random_zonotopes(rng, 257, n, 0, 14, 0.0, 1.0, 0.05)
+        if name.startswith("ACC"):
+            C += np.array([90.0, 32.0, 0.0, 10.0, 30.0, 0.0])
+        l0 = ctx.launch_count
+        got = ctx.deepz_zonotopes(dn, C, off, G, pre=pre, post=post, stats=False, hull=True)
+        assert ctx.launch_count - l0 == 1, name                      # ONE kernel: no pilot, no retry pass
+        ref = _oracle().deepz_zonotopes(on, C, off, G, pre=pre, post=post)
+        scale = max(1.0, np.abs(ref["hi"]).max(), np.abs(ref["lo"]).max())
+        np.testing.assert_allclose(got["lo"], ref["lo"], rtol=0, atol=BOX_ATOL * scale, err_msg=name)
+        np.testing.assert_allclose(got["hi"], ref["hi"], rtol=0, atol=BOX_ATOL * scale, err_msg=name)
+        np.testing.assert_array_equal(got["hull_lo"], got["lo"].min(0))
+        np.testing.assert_array_equal(got["hull_hi"], got["hi"].max(0))
+        ctx.set_tiny(False)
+        try:
+            tiled = ctx.deepz_zonotopes(dn, C, off, G, pre=pre, post=post, stats=False)
+        finally:
+            ctx.set_tiny(True)
+        np.testing.assert_allclose(got["lo"], tiled["lo"], rtol=0, atol=1e-12 * scale)
+        np.testing.assert_allclose(got["hi"], tiled["hi"], rtol=0, atol=1e-12 * scale)
+        # the padded layout and a single zonotope (the C1 case: one cell per control period)
+        one = ctx.deepz_zonotopes(dn, C[:1], off[:2], G[:off[1]], pre=pre, post=post, stats=False)
+        assert np.array_equal(one["lo"], got["lo"][:1]) and np.array_equal(one["hi"], got["hi"][:1])
+    # box grid with a flat dimension and a cut-point partition, 50 000 cells, shards bit-identical
+    net = load_net("InvertedPendulum")
+    dn = ctx.upload(net)
+    g = clr_b200.split_box([1.0, 0.0], [1.2, 0.2], [250, 200])
+    full = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, stats=False, hull=True)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g.partition, g.centers, g.radii, cell_begin=31000, cell_count=3000)
+    np.testing.assert_allclose(full["lo"][31000:34000], ref["lo"], rtol=0, atol=BOX_ATOL)
+    np.testing.assert_allclose(full["hi"][31000:34000], ref["hi"], rtol=0, atol=BOX_ATOL)
+    part = ctx.deepz_boxgrid(dn, g.partition, g.centers, g.radii, cell_begin=12345, cell_count=777, stats=False)
+    assert np.array_equal(part["lo"], full["lo"][12345:13122]) and np.array_equal(part["hi"], full["hi"][12345:13122])
+    assert full["hull_lo"][0] == full["lo"].min()
+    g2 = clr_b200.split_box([1.0, 0.1], [1.2, 0.1], [4, 1])
+    flat = ctx.deepz_boxgrid(dn, g2.partition, g2.centers, g2.radii, stats=False)
+    ref = _oracle().deepz_boxgrid(_oracle().Net(net.as_tuples()), g2.partition, g2.centers, g2.radii)
+    _cmp_boxes(flat, ref)
+    # statistics or kept zonotopes: the tiled kernel, same boxes to rounding
+    st = ctx.deepz_boxgrid(dn, g2.partition, g2.centers, g2.radii, stats=True)
+    np.testing.assert_allclose(st["lo"], flat["lo"], rtol=0, atol=1e-13)

@@ -267,3 +267,15 @@ def test_cost_weighted_bounds():
         cum = lambda x: sum(ci * (min(x, e[i + 1]) - e[i]) for i, ci in enumerate(c) if x > e[i])
         costs = [cum(b[r + 1]) - cum(b[r]) for r in range(W)]
         assert max(costs) - min(costs) <= 2.0 * 1000 + 1e-9
+
+
+def test_julia_shim_wraps_every_exported_symbol():
+    """julia/ClrB200.jl holds a `ccall` for every symbol include/clr_b200.h declares; the Julia files
+    cannot be executed in this image, so at least the binding surface is checked for completeness."""
+    import re
+    src = open(os.path.join(ROOT, "julia", "ClrB200.jl")).read()
+    bound = set(re.findall(r"\(:(clr_[a-z0-9_]+), LIB\)", src))
+    missing = sorted(set(_header_symbols()) - bound)
+    assert not missing, f"no Julia wrapper for {missing}"
+    for f in ("solve_b200.jl", "simulate_b200.jl"):
+        assert os.path.exists(os.path.join(ROOT, "julia", f))
