@@ -119,6 +119,8 @@ struct clr_ctx {
     int* h_live = nullptr;               // pinned
     long long* d_pilot = nullptr;
     int reorder = 1;                     // clr_set_reorder
+    int wide_mode = 0;                   // CLR_B200_WIDE=1: the several-threads-per-neuron relaxation in the lean kernel too (experiments)
+    bool debug = false;                  // CLR_B200_DEBUG: one line per DeepZ launch on stderr
     int tiny = 1;                        // clr_set_tiny: narrow networks take the one-warp-per-cell kernel
     // optional per-pass timing of the last DeepZ call (clr_set_profiling)
     int profiling = 0;
@@ -539,11 +541,17 @@ int launch_deepz(clr_ctx* ctx, bool global, bool stats, const Compiled* c, int g
         full = full || d.act == CLR_ACT_SIGMOID || d.act == CLR_ACT_TANH || d.ksteps > ksreg;
     }
     full = full || !c->inplace;                 // two-buffer products (a layer wider than 128 neurons)
+    // the several-threads-per-neuron relaxation: measured to pay in the global-store pass only (one wide cell per tile, every
+    // access an L2 round trip: 136 -> 124 ms in the dense regime of C4), not in shared-memory tiles (dense main pass 305 ms either
+    // way, C3 Quadrotor 4 % slower); CLR_B200_WIDE=1 switches it on for the lean kernel too (experiments)
+    const bool wide = global || ctx->wide_mode == 1;
+    if (ctx->debug) fprintf(stderr, "[clr] deepz launch: pass %d global %d stats %d full %d wide %d fuse %d grid %d\n",
+                            sp.pass, (int)global, (int)stats, (int)full, (int)wide, sp.fuse_tail, grid);
     switch (ksreg) {   // one translation unit per KSREG (deepz_ks*.cu), so that the instantiations compile in parallel
-        case 8: e = launch_deepz_ks8(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        case 16: e = launch_deepz_ks16(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        case 25: e = launch_deepz_ks25(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
-        default: e = launch_deepz_ks32(global, stats, full, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 8: e = launch_deepz_ks8(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 16: e = launch_deepz_ks16(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        case 25: e = launch_deepz_ks25(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
+        default: e = launch_deepz_ks32(global, stats, full, wide, grid, threads, smem, ctx->stream, net, in, out, ctx->d_state, sp); break;
     }
     if (e != cudaSuccess) return fail(ctx, CLR_ERR_CUDA, "DeepZ kernel launch failed: %s", cudaGetErrorString(e));
     ctx->launches++;
@@ -730,7 +738,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         // rows (the folded post-processing) that the reference does not follow by remove_zero_columns; kept zonotopes need the
         // real columns
         const DevLayer& lt = D.layer[D.L - 1];
-        sp.fuse_tail = D.L >= 2 && lt.act == CLR_ACT_ID && lt.m <= 4 && lt.n <= 4 && !lt.remove_zero && keep_cap == 0;
+        sp.fuse_tail = D.L >= 2 && lt.act == CLR_ACT_ID && lt.m <= 4 && !lt.remove_zero && keep_cap == 0;
     }
     sp.retry_list = ctx->d_retry;
     sp.big_list = ctx->d_big;
@@ -891,6 +899,8 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     c->device = device;
     c->sms = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* wv = getenv("CLR_B200_WIDE")) c->wide_mode = atoi(wv) != 0;
+    c->debug = getenv("CLR_B200_DEBUG") != nullptr;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(DevCallState));

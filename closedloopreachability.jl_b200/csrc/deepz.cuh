@@ -33,12 +33,14 @@
 #define DZ_T(i) do { } while (0)
 #endif
 
+//@phase: product (dz_gemm)
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
 
+//@phase: relaxation
 __device__ __forceinline__ bool dz_approxzero(double x) { return fabs(x) <= CLR_ZTOL; }
 __device__ __forceinline__ bool dz_approx(double x, double y) {
     if (dz_approxzero(x) && dz_approxzero(y)) return true;
@@ -46,6 +48,7 @@ __device__ __forceinline__ bool dz_approx(double x, double y) {
 }
 __device__ __forceinline__ bool dz_leq(double x, double y) { return x <= y || dz_approx(x, y); }
 
+//@phase: output
 __device__ __forceinline__ void atomicMinD(double* addr, double v) {
     unsigned long long* a = (unsigned long long*)addr;
     unsigned long long old = *a;
@@ -72,6 +75,7 @@ __device__ __forceinline__ void atomicMaxD(double* addr, double v) {
 // (tile, layer) by one thread with cp.async.bulk (SASS UBLKCP) and completed on an mbarrier; the k-loop then reads it with
 // conflict-free LDS.64.  Only when the image fits the staging area the host reserved (DeepzSched::astage_bytes).
 // ---------------------------------------------------------------------------------------------
+//@phase: product (dz_gemm)
 __device__ __forceinline__ unsigned dz_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dz_mbar_init(unsigned long long* bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(dz_smem_u32(bar)));
@@ -245,6 +249,7 @@ __device__ __forceinline__ void dz_gemm(const DevLayer& L, const double* X, doub
     }
 }
 
+//@phase: relaxation
 __device__ __forceinline__ double dz_sigm(double x) { return 1.0 / (1.0 + exp(-x)); }
 __device__ __forceinline__ double dz_sigm_p(double x) { double ex = exp(x); return ex / ((1.0 + ex) * (1.0 + ex)); }
 __device__ __forceinline__ double dz_tanh_p(double x) { double t = tanh(x); return 1.0 - t * t; }
@@ -252,6 +257,7 @@ __device__ __forceinline__ double dz_tanh_p(double x) { double t = tanh(x); retu
 // Column layout of a tile from per-cell widths, computed redundantly by every warp (no serial
 // section): lane i holds the widths of cells i and i + 32 and gets their offsets back;
 // `keep` = number of leading cells that fit into capCols columns, `total` their columns.
+//@phase: layout
 __device__ __forceinline__ void dz_layout(int w0, int w1, int nCells, int capCols, int lane, int& off0, int& off1,
                                           int& keep, int& total) {
     int s0 = w0, s1 = w1;
@@ -298,6 +304,7 @@ __device__ __forceinline__ void dz_defer(const DeepzSched& sp, DevCallState* st,
 // stays zero and contributes nothing), they are only marked so that generator counts, statistics
 // and fetched zonotopes agree with the reference.  Marks the used generator columns of the
 // current layout that are identically zero.
+//@phase: layer loop head / stats
 __device__ __forceinline__ void dz_mark_dead(unsigned* dead, const int* colOff, const unsigned short* wUsed, const double* X,
                                              int P, int rows, int nCells, int tid, int NT) {
     for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) dead[i] = 0;
@@ -313,6 +320,7 @@ __device__ __forceinline__ void dz_mark_dead(unsigned* dead, const int* colOff, 
     __syncthreads();
 }
 
+//@phase: relaxation
 // The activation rule of one neuron: bounds -> (new centre, slope, new generator); true when a generator is appended.
 template <bool FULL>
 __device__ __forceinline__ bool dz_rule(int act, double c, double lo, double hi, double& cn, double& la, double& mm) {
@@ -357,7 +365,9 @@ __device__ __forceinline__ bool dz_rule(int act, double c, double lo, double hi,
 // FULL = false: the lean instantiation for ReLU / Id networks whose layers all keep their W fragments in registers -- no
 // sigmoid / tanh code and no streamed (K > 4 KSREG) products.  The kernel is sensitive to its own size (registers live
 // across the relaxation, instruction fetch): the lean variant is 5 % faster on the same work.
-template <int KSREG, bool GLOBAL, bool STATS, bool FULL>
+//@phase: setup / tile fetch
+// WIDE = true adds the several-threads-per-neuron relaxation of tiles that hold one or two wide cells (see the relaxation).
+template <int KSREG, bool GLOBAL, bool STATS, bool FULL, bool WIDE>
 __global__ void __launch_bounds__(DZ_THREADS, DZ_CTAS)
 deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, DevCallState* st, DeepzSched sp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -469,6 +479,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         if (needDead) for (int i = tid; i < CLR_NCOL_MAX / 32; i += NT) { S.deadMask[0][i] = 0; S.deadMask[1][i] = 0; }
         __syncthreads();
 
+//@phase: input + first layer
         // ---- input zonotopes -> column store -------------------------------------------------------------------
         int flip = 0, flipD = 0;
         int nCols;
@@ -599,6 +610,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         }
         DZ_T(0);
 
+//@phase: layer loop head / stats
         // ---- layers ------------------------------------------------------------------------------------------------
         // invariant at the top (parity `flip`): data in layout colOff[flip] with wUsed[flip] columns per cell, generators
         // appended by the previous relaxation pending in mask[flip] / stage, next layout in colOff[flip ^ 1], colPos maps
@@ -634,6 +646,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 dz_gemm<KSREG, FULL>(Ly, cur, oth, P, nCols, S.kAct, colPosT, !relax, inplace, warp, lane, nWarps, a, As);
             }
             DZ_T(1);
+//@phase: appended columns
             // Pending generators mu * e_i of the previous relaxation: their image is mu * W[:, i].  In place this is safe
             // without another barrier: after the last group's barrier of the sweep every warp has read every column.
             if (l > 0) {
@@ -716,12 +729,97 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             DZ_T(2);
             const int* colOff = S.colOff[flip ^ 1];
 
+//@phase: relaxation
             // ---- relaxation: bounds, lambda, mu, rows scaled in place; thread = (cell slot, row) ------------------------
+            // The radius of a neuron is DEFINED chunk-wise: rad = ((S_0 + S_1) + S_2) + ..., S_c the ascending sum of |g_j| over
+            // the generators 64 c + 1 .. 64 c + 64 -- for cells of up to 64 generators LazySets' plain ascending sum, for wider
+            // cells the same terms grouped by 64 (a difference of rounding only, ~1e-16).  The definition does not depend on how
+            // a tile is relaxed, so a cell gets the same bits in every tile, pass and instantiation.
             if (relax) {
                 unsigned rowLive = 0;                     // 1 + the highest row this thread left non-zero
                 const int G = NT / rowsP;                 // cell slots processed side by side
                 const int slot = tid / rowsP, r = tid - slot * rowsP;
-                if (slot < G && r < m) {
+                // Tiles of one or two wide cells (the dense regime, sigmoid / tanh controllers) would leave most cell slots idle
+                // behind a chain of hundreds of dependent additions: there T = G / nCells threads share a neuron, one chunk of 64
+                // generators at a time; the partial sums go through the 8 slack columns behind the layout.
+                int T = 1;
+                if (WIDE && nCells * 2 <= G) {
+                    int wmax = 0;
+                    for (int ci = 0; ci < nCells; ci++) wmax = max(wmax, (int)wCur[ci] + (int)S.uPend[flip][ci]);
+                    if (wmax > 65 && ((wmax + 62) >> 6) * nCells <= 8) T = G / nCells;
+                }
+                if (WIDE && T > 1) {
+                    const int chCap = 8 / nCells;             // chunk slots per cell in the slack columns
+                    const int ci = slot / T, sub = slot - ci * T;
+                    const bool on = ci < nCells && r < m;
+                    double* part = cur + (size_t)colOff[nCells] * P;
+                    int w = 0, nch = 0;
+                    double* y = cur;
+                    double c = 0.0;
+                    if (on) {
+                        w = wCur[ci] + S.uPend[flip][ci];
+                        nch = (w + 62) >> 6;
+                        y = cur + colOff[ci] * P + r;
+                        c = y[0] + __ldg(Ly.bias + r);
+                        for (int ch = sub; ch < nch; ch += T) {
+                            const int j1 = min(w, 65 + 64 * ch);
+                            double sacc = 0.0;
+                            for (int j0 = 1 + 64 * ch; j0 < j1; j0 += 8) {
+                                double t[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) t[q] = j0 + q < j1 ? y[(j0 + q) * P] : 0.0;
+#pragma unroll
+                                for (int q = 0; q < 8; q++) sacc += fabs(t[q]);
+                            }
+                            part[(ci * chCap + ch) * P + r] = sacc;
+                        }
+                    }
+                    __syncthreads();   // [2a] partial sums complete; every centre has been read
+                    // ReLU: all T threads of a neuron evaluate the (cheap) rule themselves; sigmoid / tanh (four transcendental
+                    // calls): thread 0 of the neuron does and hands the slope over through the neuron's first partial-sum slot
+                    const bool shareRule = FULL && (act == CLR_ACT_SIGMOID || act == CLR_ACT_TANH);
+                    double la = 1.0;
+                    if (on && (!shareRule || sub == 0)) {
+                        double rad = nch > 0 ? part[(ci * chCap) * P + r] : 0.0;
+                        for (int ch = 1; ch < nch; ch++) rad += part[(ci * chCap + ch) * P + r];
+                        const double lo = c - rad, hi = c + rad;
+                        double cn, mm;
+                        const bool unst = dz_rule<FULL>(act, c, lo, hi, cn, la, mm);     // the same values in all T threads of a neuron
+                        if (sub == 0) {
+                            if (STATS && act == CLR_ACT_RELU && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
+                            if (cn != 0.0 || la != 0.0) {
+                                rowLive = r + 1;
+                                if (out.liveCount) atomicAdd(&out.liveCount[l * CLR_MAX_ROWS + r], 1);
+                            }
+                            y[0] = cn;
+                            if (collapse) y[P] = la * rad;
+                            if (unst) {
+                                stage[ci * stageW + r] = mm;
+                                atomicOr(&fresh[ci * mS + (r >> 5)], 1u << (r & 31));
+                            }
+                            if (shareRule) part[(ci * chCap) * P + r] = la;
+                        }
+                    }
+                    if (shareRule) {
+                        __syncthreads();   // [2b]
+                        if (on && sub != 0) la = part[(ci * chCap) * P + r];
+                    }
+                    if (on && !collapse && la != 1.0) {
+                        for (int ch = sub; ch < nch; ch += T) {
+                            const int j1 = min(w, 65 + 64 * ch);
+                            if (la == 0.0) { for (int j = 1 + 64 * ch; j < j1; j++) y[j * P] = 0.0; }
+                            else {
+                                for (int j0 = 1 + 64 * ch; j0 < j1; j0 += 8) {
+                                    double t[8];
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) t[q] = j0 + q < j1 ? y[(j0 + q) * P] : 0.0;
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) if (j0 + q < j1) y[(j0 + q) * P] = t[q] * la;
+                                }
+                            }
+                        }
+                    }
+                } else if (slot < G && r < m) {
                     const double bias = __ldg(Ly.bias + r);
                     for (int ci = slot; ci < nCells; ci += G) {
                         const int w = wCur[ci] + S.uPend[flip][ci];
@@ -737,12 +835,25 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         double rad = 0.0;
 #pragma unroll
                         for (int q = 0; q < 8; q++) rad += fabs(v[q]);       // + 0.0 beyond w: exact
-                        for (int j0 = 9; j0 < w; j0 += 8) {
+                        const int wA = min(w, 65);
+                        for (int j0 = 9; j0 < wA; j0 += 8) {
                             double t[8];
 #pragma unroll
                             for (int q = 0; q < 8; q++) t[q] = j0 + q < w ? y[(j0 + q) * P] : 0.0;
 #pragma unroll
                             for (int q = 0; q < 8; q++) rad += fabs(t[q]);
+                        }
+                        for (int jc = 65; jc < w; jc += 64) {            // further chunks of 64 generators (wide cells only)
+                            const int j1 = min(w, jc + 64);
+                            double sacc = 0.0;
+                            for (int j0 = jc; j0 < j1; j0 += 8) {
+                                double t[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) t[q] = j0 + q < j1 ? y[(j0 + q) * P] : 0.0;
+#pragma unroll
+                                for (int q = 0; q < 8; q++) sacc += fabs(t[q]);
+                            }
+                            rad += sacc;
                         }
                         const double lo = c - rad, hi = c + rad;
                         if (STATS && act == CLR_ACT_RELU && (fabs(lo) < 1e-12 || fabs(hi) < 1e-12)) atomicAdd(&S.cellNear[ci], 1u);
@@ -779,17 +890,60 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 S.kActNew = m;                            // no relaxation: every row may be non-zero
             }
             DZ_T(3);
+//@phase: layout
             // ---- next layout (every warp computes it; warp 0 publishes it) and the position table -----------------------
             if (l + 1 == Lrun) {
-                // no product follows the last layer: only the widths the output stage reads
-                if (tid < nCells) {
-                    int u = 0;
-                    for (int ww = 0; ww < mw; ww++) u += __popc(fresh[tid * mS + ww]);
-                    S.wUsed[flip ^ 1][tid] = (unsigned short)(collapse ? 2 : wCur[tid] + S.uPend[flip][tid]);
-                    S.uPend[flip ^ 1][tid] = (unsigned short)u;
-                    if (STATS && Ly.net_layer >= 0) S.cellUnst[tid][Ly.net_layer] = (unsigned short)u;
+                // no product follows the last layer: only the widths the output stage reads -- and, when the last layer of the
+                // network is applied in the output stage (fuse), the list of the generators just appended (cell, row, rank)
+                int uu[2] = {0, 0};
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int ci = lane + 32 * h;
+                    if (ci < nCells) for (int ww = 0; ww < mw; ww++) uu[h] += __popc(fresh[ci * mS + ww]);
+                }
+                int s0 = uu[0], s1 = uu[1];                  // inclusive scan over the cells: first item of every cell
+                if (fuse) {
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const int t0 = __shfl_up_sync(0xffffffffu, s0, dd);
+                        const int t1 = __shfl_up_sync(0xffffffffu, s1, dd);
+                        if (lane >= dd) { s0 += t0; s1 += t1; }
+                    }
+                    s1 += __shfl_sync(0xffffffffu, s0, 31);
+                }
+                const int ub0 = s0 - uu[0], ub1 = s1 - uu[1];
+                if (warp == 0) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int ci = lane + 32 * h;
+                        if (ci < nCells) {
+                            S.wUsed[flip ^ 1][ci] = (unsigned short)(collapse ? 2 : wCur[ci] + S.uPend[flip][ci]);
+                            S.uPend[flip ^ 1][ci] = (unsigned short)uu[h];
+                            if (fuse) S.uPend[flip][ci] = (unsigned short)(h ? ub1 : ub0);     // the array just read is free: item base of the cell
+                            if (STATS && Ly.net_layer >= 0) S.cellUnst[ci][Ly.net_layer] = (unsigned short)uu[h];
+                        }
+                    }
                 }
                 if (tid == 0) S.kAct = S.kActNew;
+                if (fuse) {
+                    const int nIt = __shfl_sync(0xffffffffu, nCells <= 32 ? s0 : s1, (nCells - 1) & 31);
+                    if (tid == 0) S.nItems = nIt;
+                    if (nIt <= DZ_ITEMS_MAX) {
+                        for (int ci = warp; ci < nCells; ci += nWarps) {
+                            const int base = ci < 32 ? __shfl_sync(0xffffffffu, ub0, ci & 31) : __shfl_sync(0xffffffffu, ub1, ci & 31);
+                            int before = 0;
+                            for (int ww = 0; ww < mw; ww++) {
+                                const unsigned bits = fresh[ci * mS + ww];
+                                if ((bits >> lane) & 1u) {
+                                    const int k = before + __popc(bits & ((1u << lane) - 1u));
+                                    S.itemCell[base + k] = (unsigned short)ci;
+                                    S.itemRow[base + k] = (unsigned short)(ww * 32 + lane);
+                                }
+                                before += __popc(bits);
+                            }
+                        }
+                    }
+                }
             } else {
                 int off0, off1, keep, total;
                 int w[2] = {0, 0}, wu[2] = {0, 0}, uu[2] = {0, 0};
@@ -892,6 +1046,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
         }
         if (tileDead) continue;
 
+//@phase: output
         // ---- outputs ---------------------------------------------------------------------------------------------------
         {
             const int* colOff = S.colOff[flip];
@@ -909,26 +1064,49 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     S.cellPin[tid][Lt.net_layer] = (unsigned short)nz;
                     S.cellUnst[tid][Lt.net_layer] = 0;
                 }
-                // W x for every used column, in place: rows 0 .. mt-1 of the column become its image.  The fused layer has
-                // at most 4 inputs (post-processing, or a layer behind a one-row layer): a thread per column, k ascending.
+                // W x for every used column, in place: rows 0 .. mt-1 of the column become its image (a thread per column, k
+                // ascending; rows >= kAct of the store are zero).  The fused layer has at most 4 rows: the scalar control of most
+                // models, or the folded post-processing.
+                const int kA = min(nt, S.kAct);
                 for (int col = tid; col < nCols; col += NT) {
                     int lo_ = 0, hi_ = nCells;                 // cell of this column: the last ci with colOff[ci] <= col
                     while (hi_ - lo_ > 1) { const int mid = (lo_ + hi_) >> 1; if (colOff[mid] <= col) lo_ = mid; else hi_ = mid; }
                     const int j = col - colOff[lo_];
                     if (j >= S.wUsed[flip][lo_]) continue;
                     double* x = cur + col * P;
-                    double xv[4], yv[4];
+                    double yv[4];
+                    if (nt <= 4) {
+                        double xv[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) xv[k] = k < nt ? x[k] : 0.0;
+                        for (int k = 0; k < 4; k++) xv[k] = k < nt ? x[k] : 0.0;
 #pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        double sacc = 0.0;
+                        for (int r = 0; r < 4; r++) {
+                            double sacc = 0.0;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) if (k < nt && r < mt) sacc += __ldg(Lt.Wcm + (size_t)k * mt + r) * xv[k];
-                        yv[r] = (j == 0 && r < mt) ? sacc + __ldg(Lt.bias + r) : sacc;
+                            for (int k = 0; k < 4; k++) if (k < nt && r < mt) sacc += __ldg(Lt.Wcm + (size_t)k * mt + r) * xv[k];
+                            yv[r] = sacc;
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) yv[r] = 0.0;
+#pragma unroll 4
+                        for (int k = 0; k < kA; k++) {
+                            const double xk = x[k];
+#pragma unroll
+                            for (int r = 0; r < 4; r++) if (r < mt) yv[r] += __ldg(Lt.Wcm + (size_t)k * mt + r) * xk;
+                        }
                     }
 #pragma unroll
-                    for (int r = 0; r < 4; r++) if (r < mt) x[r] = yv[r];
+                    for (int r = 0; r < 4; r++) if (r < mt) x[r] = j == 0 ? yv[r] + __ldg(Lt.bias + r) : yv[r];
+                }
+                // images mu_i W[:, i] of the generators appended by the last relaxation, item-major in the 8 slack columns
+                // behind the layout (when the tile's list fits; otherwise the output loops walk the row masks)
+                if (S.nItems <= DZ_ITEMS_MAX && S.nItems * mt <= 8 * P) {
+                    double* img = cur + (size_t)nCols * P;
+                    for (int t = tid; t < S.nItems * mt; t += NT) {
+                        const int item = t / mt, r = t - item * mt, i = S.itemRow[item];
+                        img[t] = stage[S.itemCell[item] * stageW + i] * __ldg(Lt.Wcm + (size_t)i * mt + r);
+                    }
                 }
                 __syncthreads();
             }
@@ -963,6 +1141,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 const bool pend = !fuse && ((mwv >> (r & 31)) & 1u);     // this row's own appended generator mu * e_r
                 const double mu = pend ? stage[ci * stageW + r] : 0.0;
                 double c = y[0], lo, hi;
+                if (fuse && (w - 1) + (int)S.uPend[flip][ci] > 64) continue;     // wide cell: summed by a whole warp below
                 if (fuse) {
                     // the columns hold W x already; the generators appended by the last relaxation are mu_i e_i, their
                     // images mu_i W[r, i] come after them, in ascending i (the order of the materialised columns)
@@ -1023,6 +1202,49 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         if (k0 + k < out.keep_cap) g[(size_t)(k0 + k) * mOut] = (pend && k == rank) ? mu : 0.0;
                 }
             }
+            if (fuse) {
+                // Cells of more than 64 generators: a warp per (cell, output row).  The radius is DEFINED as the sum over the lanes
+                // (fixed butterfly) of each lane's ascending sum over the generators g = lane, lane + 32, ... of the list
+                // [materialised columns | appended generators in ascending row order] -- the same for every tile and pass.
+                const int mt = Lt.m, mwN = (Lt.n + 31) >> 5;
+                const bool listed = S.nItems <= DZ_ITEMS_MAX && S.nItems * mt <= 8 * P;
+                const double* img = cur + (size_t)nCols * P;
+                const unsigned short* ibase = S.uPend[flip ^ 1];
+                for (int task = warp; task < nCells * mOut; task += nWarps) {
+                    const int ci = task / mOut, r = task - ci * mOut;
+                    const int w = S.wUsed[flip][ci], p = (w - 1) + (int)S.uPend[flip][ci];
+                    if (p <= 64) continue;
+                    const double* y = cur + colOff[ci] * P + r;
+                    double acc = 0.0;
+                    if (listed) {
+                        const double* im = img + (size_t)ibase[ci] * mt + r;
+                        for (int g = lane; g < p; g += 32) acc += fabs(g < w - 1 ? y[(g + 1) * P] : im[(g - (w - 1)) * mt]);
+                    } else {
+                        for (int g = lane; g < w - 1; g += 32) acc += fabs(y[(g + 1) * P]);
+                        int g = w - 1;
+                        for (int ww = 0; ww < mwN; ww++) {
+                            unsigned bits = maskBase[flip * maskHalf + ci * mS + ww];
+                            while (bits) {
+                                const int i = ww * 32 + __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                if ((g & 31) == lane) acc += fabs(stage[ci * stageW + i] * __ldg(Lt.Wcm + (size_t)i * mt + r));
+                                g++;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                    if (lane == 0) {
+                        const double c = y[0], lo = c - acc, hi = c + acc;
+                        const long long cell = S.cellId[ci];
+                        if (out.out_lo) { out.out_lo[cell * mOut + r] = lo; out.out_hi[cell * mOut + r] = hi; }
+                        if (out.hull_lo) {
+                            if (useHull) { atomicMinD(&S.hlo[r], lo); atomicMaxD(&S.hhi[r], hi); }
+                            else { atomicMinD(&out.hull_lo[r], lo); atomicMaxD(&out.hull_hi[r], hi); }
+                        }
+                    }
+                }
+            }
             if (STATS) {
                 __syncthreads();
                 if (tid < nCells) {
@@ -1038,6 +1260,7 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
             }
         }
         DZ_T(5);
+//@phase: tile size / tail
         // ---- adapt the tile size to the growth just seen ---------------------------------------------------------------
         if (tid == 0) {
             if (sp.tile_cells <= 0 && sp.pass != 2) {

@@ -3,7 +3,7 @@
 #include "deepz_types.cuh"
 
 #define DZ_LAUNCH_ARGS                                                                                          \
-    bool global, bool stats, bool full, int grid, int threads, size_t smem, cudaStream_t stream, const DevNet *net,        \
+    bool global, bool stats, bool full, bool wide, int grid, int threads, size_t smem, cudaStream_t stream, const DevNet *net,        \
         const DeepzInput &in, const DeepzOutput &out, DevCallState *st, const DeepzSched &sp
 cudaError_t launch_deepz_ks8(DZ_LAUNCH_ARGS);
 cudaError_t launch_deepz_ks16(DZ_LAUNCH_ARGS);

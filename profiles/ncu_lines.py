@@ -6,14 +6,32 @@
 ncu does not escape quotes inside the source-text column (a line such as `: "d"(a), "d"(b));` shifts the columns of a naive CSV
 parse -- round 1's summary attributed the DMMA line's `math` stalls to `membar` that way).  The numeric columns are therefore
 addressed from the END of each row.  With a third argument "phases" the samples are also summed per phase of deepz_kernel
-(line ranges of deepz.cuh given in PHASES).
+(line ranges of deepz.cuh between its `//@phase:` markers).
 """
 import sys
 from collections import defaultdict
 
-PHASES = [("product (dz_gemm)", 36, 41), ("product (dz_gemm)", 68, 215), ("setup / tile fetch", 290, 398), ("input + first layer", 399, 524),
-          ("layer loop head / stats", 525, 552), ("appended columns", 553, 633), ("relaxation", 634, 749), ("layout", 750, 860),
-          ("output", 861, 1010), ("tile size / tail", 1011, 1060)]
+import os
+import re
+
+
+def load_phases():
+    """Phase of every line of deepz.cuh, from its `//@phase: <name>` markers (a phase runs up to the next marker)."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "closedloopreachability.jl_b200", "csrc", "deepz.cuh")
+    out, cur, start = [], None, 1
+    lines = open(path).read().split("\n")
+    for no, ln in enumerate(lines, 1):
+        m = re.match(r"\s*//@phase:\s*(.+)$", ln)
+        if m:
+            if cur:
+                out.append((cur, start, no - 1))
+            cur, start = m.group(1).strip(), no
+    if cur:
+        out.append((cur, start, len(lines)))
+    return out
+
+
+PHASES = load_phases()
 
 
 def split_row(line):
