@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cstring>
 #include <dlfcn.h>
 #include <limits>
@@ -74,8 +76,8 @@ struct clr_plant {
     clr_ctx* ctx = nullptr;
     int ns = 0, nd = 0, nc = 0;
     std::string source;             // prelude + rollout.cuh + the user's right-hand side
-    cudaLibrary_t lib[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaKernel_t kern[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaLibrary_t lib[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};      // slot 5: rollout_ode_kernel (split rollouts)
+    cudaKernel_t kern[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct clr_ctx {
@@ -122,6 +124,7 @@ struct clr_ctx {
     int wide_mode = 0;                   // CLR_B200_WIDE=1: the several-threads-per-neuron relaxation in the lean kernel too (experiments)
     bool debug = false;                  // CLR_B200_DEBUG: one line per DeepZ launch on stderr
     int tiny = 1;                        // clr_set_tiny: narrow networks take the one-warp-per-cell kernel
+    int ro_split = 1;                    // CLR_B200_RO_SPLIT=0: narrow controllers stay in the fused rollout kernel (experiments)
     // optional per-pass timing of the last DeepZ call (clr_set_profiling)
     int profiling = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -414,6 +417,8 @@ int compile_layers(clr_ctx* ctx, const std::vector<HostLayer>& layers, int n_in,
             }
         }
         P.stotal = (int)simg.size();
+        static std::atomic<long long> next_serial{1};
+        P.sserial = next_serial.fetch_add(1);
         if ((rc = upload(ctx, c, simg, &P.simage))) { free_compiled(c); return rc; }
     }
     const int ks_opts[4] = {8, 16, 25, 32};
@@ -901,6 +906,7 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* wv = getenv("CLR_B200_WIDE")) c->wide_mode = atoi(wv) != 0;
     c->debug = getenv("CLR_B200_DEBUG") != nullptr;
+    if (const char* v = getenv("CLR_B200_RO_SPLIT")) c->ro_split = atoi(v) != 0;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(DevCallState));
@@ -1548,10 +1554,108 @@ int launch_rollout_blocked(clr_ctx* ctx, const PointNet& P, const RolloutArgs& A
     return 0;
 }
 
+// ---- split rollouts (rollout.cuh: controller_cw_kernel + rollout_ode_kernel) -------------------------------------------
+// The constant-bank copy of a packed controller (ro_cw) is one per device: a call that needs another image replaces it
+// behind the last kernel that read the old one (events order the streams of different contexts on one device).
+struct ConstBank {
+    std::mutex mu;
+    long long serial = 0;            // PointNet::sserial of the resident image, 0 = none
+    cudaEvent_t ready = nullptr;     // recorded behind the copy
+    cudaEvent_t last_use = nullptr;  // recorded behind the most recent kernel that reads the bank
+};
+#define CLR_CBANK_DEVICES 64
+ConstBank g_cbank[CLR_CBANK_DEVICES];
+
+// with B.mu held: make P's packed image the resident one, ordered on ctx->stream
+int cbank_acquire(clr_ctx* ctx, ConstBank& B, const PointNet& P) {
+    if (!B.ready) {
+        CU(cudaEventCreateWithFlags(&B.ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&B.last_use, cudaEventDisableTiming));
+    }
+    if (B.serial != P.sserial) {
+        if (B.serial) CU(cudaStreamWaitEvent(ctx->stream, B.last_use, 0));
+        B.serial = 0;
+        CU(cudaMemcpyToSymbolAsync(ro_cw, P.simage, sizeof(double) * (size_t)P.stotal, 0, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaEventRecord(B.ready, ctx->stream));
+        B.serial = P.sserial;
+    } else {
+        CU(cudaStreamWaitEvent(ctx->stream, B.ready, 0));
+    }
+    return 0;
+}
+
+template <int NI, int NO>
+int launch_ctrl_cw_n(clr_ctx* ctx, const PointNet& P, int nx, int64_t N, const double* X, double* U) {
+    // 4 points per thread, 4 blocks per SM, records fetched one neuron ahead: the best of the variants measured on B200
+    // (2 / 6 / 8 points per thread, 5 / 6 blocks per SM with their spills: profiles/r02/rollout_split_variants_b200.txt)
+    constexpr int R = 4;
+    const int64_t span = 128 * R;
+    controller_cw_kernel<NI, NO, R, 4, true><<<(unsigned)((N + span - 1) / span), 128, 0, ctx->stream>>>(P, nx, (long long)N, X, U);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+int launch_ctrl_cw(clr_ctx* ctx, int code, const PointNet& P, int nx, int64_t N, const double* X, double* U) {
+    switch (code) {
+        case 66: return launch_ctrl_cw_n<4, 2>(ctx, P, nx, N, X, U);
+        case 72: return launch_ctrl_cw_n<4, 8>(ctx, P, nx, N, X, U);
+        default: return launch_ctrl_cw_n<8, 8>(ctx, P, nx, N, X, U);
+    }
+}
+
+bool split_eligible(const clr_ctx* ctx, int code, const PointNet& P, int64_t N) {
+    return ctx->ro_split && code > 2 && P.L <= RO_CW_LAYERS && P.stotal + 32 <= RO_CW_DOUBLES && ctx->device < CLR_CBANK_DEVICES && N <= (int64_t)1 << 38;
+}
+
+// `ode`: launches one control period of the plant (built-in template or the run-time compiled kernel)
+template <class OdeLaunch>
+int rollout_split(clr_ctx* ctx, int code, const PointNet& P, const RolloutArgs& A, int ns, int nc, OdeLaunch ode) {
+    ConstBank& B = g_cbank[ctx->device];
+    std::lock_guard<std::mutex> lock(B.mu);
+    int rc = cbank_acquire(ctx, B, P);
+    if (rc) return rc;
+    double t = A.t0;
+    for (int it = 0; it < A.iters; it++) {
+        const double* xprev = it == 0 ? A.x0 : A.X_end + (size_t)(it - 1) * A.N * ns;
+        if ((rc = launch_ctrl_cw(ctx, code, P, ns, A.N, xprev, A.U + (size_t)it * A.N * nc))) return rc;
+        const double t1 = it < A.iters - 1 ? t + A.tau : A.T;
+        if ((rc = ode(it, t, t1, xprev))) return rc;
+        t = t1;
+    }
+    CU(cudaEventRecord(B.last_use, ctx->stream));
+    return 0;
+}
+
+template <int PLANT>
+int launch_rollout_split(clr_ctx* ctx, int code, const PointNet& P, const RolloutArgs& A) {
+    constexpr int NS = PlantDims<PLANT>::NS, NC = PlantDims<PLANT>::NC;
+    const unsigned grid = (unsigned)((A.N + 127) / 128);
+    return rollout_split(ctx, code, P, A, NS, NC, [&](int it, double t, double t1, const double* xprev) -> int {
+        rollout_ode_kernel<PLANT><<<grid, 128, 0, ctx->stream>>>(A, it, t, t1, xprev);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    });
+}
+
 // run-time compiled plant: same kernels, launched through the cudaLibrary handle of the plant
 int plant_build(clr_ctx* ctx, clr_plant* p, int slot, bool load);
 
 int launch_rollout_user(clr_ctx* ctx, const clr_plant* plant, int code, const PointNet& P, const RolloutArgs& A) {
+    if (split_eligible(ctx, code, P, A.N)) {
+        int brc = plant_build(ctx, const_cast<clr_plant*>(plant), 5, true);
+        if (brc) return brc;
+        void* fn = (void*)plant->kern[5];
+        const unsigned grid = (unsigned)((A.N + 127) / 128);
+        return rollout_split(ctx, code, P, A, plant->ns, plant->nc, [&](int it, double t, double t1, const double* xprev) -> int {
+            RolloutArgs Ac = A;
+            void* args[5] = {&Ac, &it, &t, &t1, &xprev};
+            CU(cudaLaunchKernel(fn, dim3(grid), dim3(128), args, 0, ctx->stream));
+            ctx->launches++;
+            return 0;
+        });
+    }
     int slot = 4;
     for (int i = 0; i < 5; i++) if (kPlantCodes[i] == code) slot = i;
     int brc = plant_build(ctx, const_cast<clr_plant*>(plant), slot, true);
@@ -1585,6 +1689,7 @@ int launch_rollout_user(clr_ctx* ctx, const clr_plant* plant, int code, const Po
 
 template <int PLANT>
 int launch_rollout_p(clr_ctx* ctx, int code, const PointNet& P, const RolloutArgs& A) {
+    if (split_eligible(ctx, code, P, A.N)) return launch_rollout_split<PLANT>(ctx, code, P, A);
     switch (code) {
         case 66: return launch_rollout_blocked<PLANT, 66>(ctx, P, A);
         case 72: return launch_rollout_blocked<PLANT, 72>(ctx, P, A);
@@ -1648,7 +1753,8 @@ int plant_build(clr_ctx* ctx, clr_plant* p, int slot, bool load) {
     int rc = n.CreateProgram(&prog, p->source.c_str(), "clr_user_plant.cu", 0, nullptr, nullptr);
     if (rc) return fail(ctx, CLR_ERR_STATE, "nvrtcCreateProgram: %s", n.GetErrorString(rc));
     char expr[96];
-    snprintf(expr, sizeof(expr), kPlantCodes[slot] > 2 ? "rollout_blocked_kernel<1000, %d>" : "rollout_kernel<1000, %d>", kPlantCodes[slot]);
+    if (slot == 5) snprintf(expr, sizeof(expr), "rollout_ode_kernel<1000>");
+    else snprintf(expr, sizeof(expr), kPlantCodes[slot] > 2 ? "rollout_blocked_kernel<1000, %d>" : "rollout_kernel<1000, %d>", kPlantCodes[slot]);
     n.AddNameExpression(prog, expr);
     const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo"};
     rc = n.CompileProgram(prog, 4, opts);
@@ -1717,7 +1823,7 @@ int32_t clr_plant_compile(clr_ctx* ctx, int32_t n_state, int32_t n_dist, int32_t
 void clr_plant_free(clr_plant* p) {
     if (!p) return;
     if (p->ctx) cudaSetDevice(p->ctx->device);
-    for (int i = 0; i < 5; i++) if (p->lib[i]) cudaLibraryUnload(p->lib[i]);
+    for (int i = 0; i < 6; i++) if (p->lib[i]) cudaLibraryUnload(p->lib[i]);
     delete p;
 }
 
@@ -1746,8 +1852,16 @@ int32_t clr_forward_points(clr_ctx* ctx, const clr_net* net_c, const clr_prepost
         if ((rc = ensure(ctx, &ctx->d_io[4], &ctx->io_bytes[4], sizeof(double) * (size_t)m * N))) return rc;
         dU = (double*)ctx->d_io[4];
     }
-    rc = launch_points_code(ctx, c->point_code, c->pnet, nx, N, (const double*)dX, dU);
-    if (rc) return rc;
+    if (split_eligible(ctx, c->point_code, c->pnet, N)) {
+        ConstBank& B = g_cbank[ctx->device];
+        std::lock_guard<std::mutex> lock(B.mu);
+        if ((rc = cbank_acquire(ctx, B, c->pnet))) return rc;
+        if ((rc = launch_ctrl_cw(ctx, c->point_code, c->pnet, nx, N, (const double*)dX, dU))) return rc;
+        CU(cudaEventRecord(B.last_use, ctx->stream));
+    } else {
+        rc = launch_points_code(ctx, c->point_code, c->pnet, nx, N, (const double*)dX, dU);
+        if (rc) return rc;
+    }
     if (!dev_io) {
         CU(cudaMemcpyAsync(U, dU, sizeof(double) * (size_t)m * N, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));

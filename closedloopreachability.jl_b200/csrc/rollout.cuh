@@ -32,6 +32,7 @@ struct PointNet {
     int small_ni, small_no, stotal;
     int soff[RO_MAX_LAYERS];
     const double* simage;
+    long long sserial;            // host side: identifies the packed image (which one is resident in the constant bank)
 };
 
 __device__ __forceinline__ double ro_act(int act, double s) {
@@ -357,34 +358,65 @@ struct RolloutArgs {
     int* error;            // device flag: CLR_ERR_CAPACITY when a step log overflows, CLR_ERR_UNSTABLE when an integration gave up
 };
 
-#define TS_A21 0.161
-#define TS_A31 -0.008480655492356989
-#define TS_A32 0.335480655492357
-#define TS_A41 2.8971530571054935
-#define TS_A42 -6.359448489975075
-#define TS_A43 4.3622954328695815
-#define TS_A51 5.325864828439257
-#define TS_A52 -11.748883564062828
-#define TS_A53 7.4955393428898365
-#define TS_A54 -0.09249506636175525
-#define TS_A61 5.86145544294642
-#define TS_A62 -12.92096931784711
-#define TS_A63 8.159367898576159
-#define TS_A64 -0.071584973281401
-#define TS_A65 -0.028269050394068383
-#define TS_A71 0.09646076681806523
-#define TS_A72 0.01
-#define TS_A73 0.4798896504144996
-#define TS_A74 1.379008574103742
-#define TS_A75 -3.290069515436081
-#define TS_A76 2.324710524099774
-#define TS_BT1 -0.00178001105222577714
-#define TS_BT2 -0.0008164344596567469
-#define TS_BT3 0.007880878010261995
-#define TS_BT4 -0.1447110071732629
-#define TS_BT5 0.5823571654525552
-#define TS_BT6 -0.45808210592918697
-#define TS_BT7 0.015151515151515152
+// Tsit5 tableau in the constant bank: a coefficient is then a direct c[bank][offset] operand of the FP64 instruction instead
+// of a 64-bit literal that takes two extra instructions (UMOV / IMAD.MOV) to materialise at every use
+__constant__ double ro_ts[28] = {
+    0.161,
+    -0.008480655492356989,
+    0.335480655492357,
+    2.8971530571054935,
+    -6.359448489975075,
+    4.3622954328695815,
+    5.325864828439257,
+    -11.748883564062828,
+    7.4955393428898365,
+    -0.09249506636175525,
+    5.86145544294642,
+    -12.92096931784711,
+    8.159367898576159,
+    -0.071584973281401,
+    -0.028269050394068383,
+    0.09646076681806523,
+    0.01,
+    0.4798896504144996,
+    1.379008574103742,
+    -3.290069515436081,
+    2.324710524099774,
+    -0.00178001105222577714,
+    -0.0008164344596567469,
+    0.007880878010261995,
+    -0.1447110071732629,
+    0.5823571654525552,
+    -0.45808210592918697,
+    0.015151515151515152};
+#define TS_A21 ro_ts[0]
+#define TS_A31 ro_ts[1]
+#define TS_A32 ro_ts[2]
+#define TS_A41 ro_ts[3]
+#define TS_A42 ro_ts[4]
+#define TS_A43 ro_ts[5]
+#define TS_A51 ro_ts[6]
+#define TS_A52 ro_ts[7]
+#define TS_A53 ro_ts[8]
+#define TS_A54 ro_ts[9]
+#define TS_A61 ro_ts[10]
+#define TS_A62 ro_ts[11]
+#define TS_A63 ro_ts[12]
+#define TS_A64 ro_ts[13]
+#define TS_A65 ro_ts[14]
+#define TS_A71 ro_ts[15]
+#define TS_A72 ro_ts[16]
+#define TS_A73 ro_ts[17]
+#define TS_A74 ro_ts[18]
+#define TS_A75 ro_ts[19]
+#define TS_A76 ro_ts[20]
+#define TS_BT1 ro_ts[21]
+#define TS_BT2 ro_ts[22]
+#define TS_BT3 ro_ts[23]
+#define TS_BT4 ro_ts[24]
+#define TS_BT5 ro_ts[25]
+#define TS_BT6 ro_ts[26]
+#define TS_BT7 ro_ts[27]
 
 __device__ __forceinline__ double ro_eps_of(double x) {
     x = fabs(x);
@@ -731,4 +763,160 @@ rollout_blocked_kernel(PointNet net, RolloutArgs A, int in_smem) {
             t = t1;
         }
     }
+}
+
+// ---- split rollouts: one controller launch + one plant launch per control period -----------------------------------
+// The fused kernels above evaluate a narrow controller from 128-bit broadcast loads of its packed records: four loads
+// per hidden neuron and warp = 14 cycles of the SM's 128 B/clk load-return path against the 56 cycles the neuron's 28
+// FP64 instructions take on one of the four sub-partitions -- with four sub-partitions the load path is as busy as the
+// FP64 pipe, and the adaptive integration that follows in the same kernel pins the register budget at 16 warps per SM.
+// Split, the controller kernel runs in warp-uniform control flow throughout, so ptxas keeps the record pointer in a
+// uniform register and fetches the weights from the constant bank (ro_cw) into UNIFORM registers (LDCU: one copy per
+// warp instead of 32, no load-return traffic) that feed the DFMAs directly; the plant kernel owns one trajectory per
+// thread at its own, higher occupancy.  The state travels between the two through the X_end / U arrays the call
+// returns anyway (64 B read back per trajectory and period).
+#ifndef RO_CW_DOUBLES
+#define RO_CW_DOUBLES 7168
+#endif
+#ifndef __CUDACC_RTC__
+__constant__ double ro_cw[RO_CW_DOUBLES];
+
+__device__ __noinline__ double ro_act_cold(int act, double s) { return ro_act(act, s); }
+
+template <int NI, int NO, int R, bool RELU, bool AHEAD>
+__device__ __forceinline__ void cw_pair(int off, int m, int a1, const double (&va)[R][8], double (&vb)[R][NO]) {
+    constexpr int ST = NI + NO + 2;
+    double nx[ST - 1];
+    if (AHEAD) {
+#pragma unroll
+        for (int k = 0; k < ST - 1; k++) nx[k] = ro_cw[off + k];
+    }
+#pragma unroll 2
+    for (int i = 0; i < m; i++) {
+        double rc[ST - 1];
+        if (AHEAD) {     // the record of neuron i + 1 is requested before neuron i is evaluated (after the last one: whatever
+                         // follows in the bank, unused -- the host keeps one record of head-room behind every image)
+            const double* rec = ro_cw + off + (i + 1) * ST;
+#pragma unroll
+            for (int k = 0; k < ST - 1; k++) { rc[k] = nx[k]; nx[k] = rec[k]; }
+        } else {
+            const double* rec = ro_cw + off + i * ST;
+#pragma unroll
+            for (int k = 0; k < ST - 1; k++) rc[k] = rec[k];
+        }
+        double s[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) s[r] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NI; k++) {
+#pragma unroll
+            for (int r = 0; r < R; r++) s[r] = fma(rc[k], va[r][k], s[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) { s[r] += rc[NI + NO]; s[r] = RELU ? ro_relu_bits(s[r]) : ro_act_cold(a1, s[r]); }
+#pragma unroll
+        for (int o = 0; o < NO; o++) {
+#pragma unroll
+            for (int r = 0; r < R; r++) vb[r][o] = fma(rc[NI + o], s[r], vb[r][o]);
+        }
+    }
+}
+
+// layers L0, L0 + 1 (a pair) or the single last layer L0; L0 is a literal so that every table index is one too: ptxas then
+// sees uniform addresses and keeps the record pointer in a uniform register
+template <int NI, int NO, int R, int L0, bool AHEAD>
+__device__ __forceinline__ void cw_stage(const PointNet& net, double (&va)[R][8]) {
+    if (net.L >= L0 + 2) {
+        const int m = net.dims[L0 + 1], m2 = net.dims[L0 + 2];
+        const int a1 = net.act[L0], a2 = net.act[L0 + 1];
+        const double* b2 = ro_cw + net.soff[L0 + 1];
+        double vb[R][NO];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int o = 0; o < NO; o++) vb[r][o] = 0.0;
+        if (a1 == CLR_ACT_RELU) cw_pair<NI, NO, R, true, AHEAD>(net.soff[L0], m, a1, va, vb);
+        else cw_pair<NI, NO, R, false, AHEAD>(net.soff[L0], m, a1, va, vb);
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int o = 0; o < 8; o++) va[r][o] = (o < NO && o < m2) ? ro_act_cold(a2, vb[r][o < NO ? o : 0] + b2[o < NO ? o : 0]) : 0.0;
+    } else if (net.L == L0 + 1) {
+        constexpr int ST1 = NI + 2;
+        const int m = net.dims[L0 + 1], a1 = net.act[L0];
+        const double* rec = ro_cw + net.soff[L0];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            double vb[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                vb[i] = 0.0;
+                if (i < m) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NI; k++) s = fma(rec[i * ST1 + k], va[r][k], s);
+                    vb[i] = ro_act_cold(a1, s + rec[i * ST1 + NI]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) va[r][i] = vb[i];
+        }
+    }
+}
+
+// U[j] = network(X[j]) for R points per thread (same arithmetic per point as ro_mlp_small); X: N x nx, U: N x m_out.
+// Networks of at most RO_CW_LAYERS layers (the host checks).
+#define RO_CW_LAYERS 4
+template <int NI, int NO, int R, int MINBLK, bool AHEAD>
+__global__ void __launch_bounds__(128, MINBLK)
+controller_cw_kernel(PointNet net, int nx, long long N, const double* __restrict__ X, double* __restrict__ U) {
+    const long long base = blockIdx.x * (128ll * R) + threadIdx.x;
+    double va[R][8];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        long long j = base + r * 128;
+        if (j >= N) j = N - 1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) va[r][k] = (k < NI && k < nx) ? X[j * nx + (k < NI ? k : 0)] : 0.0;
+    }
+    cw_stage<NI, NO, R, 0, AHEAD>(net, va);
+    cw_stage<NI, NO, R, 2, AHEAD>(net, va);
+    const int mo = net.m_out;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const long long j = base + r * 128;
+        if (j < N) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k < mo) U[j * mo + k] = va[r][k];
+        }
+    }
+}
+#endif  // !__CUDACC_RTC__
+
+// One control period of the plant for every trajectory: x(t) from Xprev (x0 or the previous period's X_end), the
+// control from U (written by the controller launch of this period), the disturbance from Wd.
+#ifndef RO_ODE_MINBLK
+#define RO_ODE_MINBLK 5
+#endif
+template <int PLANT>
+__global__ void __launch_bounds__(128, RO_ODE_MINBLK)
+rollout_ode_kernel(RolloutArgs A, int it, double t, double t1, const double* __restrict__ Xprev) {
+    constexpr int NS = PlantDims<PLANT>::NS, ND = PlantDims<PLANT>::ND, NC = PlantDims<PLANT>::NC;
+    const long long j = blockIdx.x * 128ll + threadIdx.x;
+    if (j >= A.N) return;
+    const long long cell = (long long)it * A.N + j;
+    double x[NS], q[ND + NC];
+#pragma unroll
+    for (int i = 0; i < NS; i++) x[i] = Xprev[j * NS + i];
+#pragma unroll
+    for (int i = 0; i < ND; i++) q[i] = A.Wd[cell * ND + i];
+#pragma unroll
+    for (int i = 0; i < NC; i++) q[ND + i] = A.U[cell * NC + i];
+    int nacc = 0, nrej = 0;
+    if (A.alg == CLR_ALG_TSIT5) ro_tsit5<PLANT>(x, q, t, t1, A, cell, nacc, nrej);
+    else { ro_rk4<PLANT>(x, q, t, t1, A.substeps); nacc = A.substeps; }
+    if (A.naccept) A.naccept[cell] = nacc;
+    if (A.nreject) A.nreject[cell] = nrej;
+#pragma unroll
+    for (int i = 0; i < NS; i++) A.X_end[cell * NS + i] = x[i];
 }

@@ -184,3 +184,69 @@ def test_runtime_compiled_plants(ctx):
     np.testing.assert_allclose(got["U"], ref["U"], rtol=0, atol=TRAJ_ATOL)
     with pytest.raises(runtime.ClrArgumentError):
         ctx.rollout(da, plant, xa, None, 0.0, 0.1, 3.0, 30)          # 6 state columns into a 4-state plant
+
+
+def _synthetic_net(dims, acts, seed):
+    import clr_b200
+    rng = np.random.default_rng(seed)
+    layers = [(rng.normal(0, 1.0 / np.sqrt(n), (m, n)), rng.normal(0, 0.3, m), a)
+              for n, m, a in zip(dims[:-1], dims[1:], acts)]
+    return clr_b200.FeedforwardNetwork.from_tuples(layers)
+
+
+# narrow controllers (every materialised vector has at most 8 entries) are evaluated from the constant bank by
+# controller_cw_kernel: every record shape (4/2, 4/8, 8/8), 1-4 layers (pair, pair + pair, pair + single tail), every activation
+NARROW = [([3, 40, 2], ["ReLU", "Id"]), ([4, 30, 4], ["Sigmoid", "Tanh"]), ([4, 25, 3, 7], ["ReLU", "ReLU", "Id"]),
+          ([4, 30, 6, 20, 5], ["Tanh", "ReLU", "ReLU", "Sigmoid"]), ([8, 8], ["ReLU"]), ([2, 512, 1], ["ReLU", "Id"])]
+
+
+@pytest.mark.parametrize("case", range(len(NARROW)))
+def test_forward_points_narrow_networks(ctx, case):
+    dims, acts = NARROW[case]
+    net = _synthetic_net(dims, acts, 40 + case)
+    for N in (1, 511, 1000):                      # not a multiple of the 512 points a block takes
+        X = np.random.default_rng(50 + N).uniform(-1, 1, (N, dims[0]))
+        got = ctx.forward_points(ctx.upload(net), X)
+        ref = _oracle().forward_points(_oracle().Net(net.as_tuples()), X)
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-13)
+
+
+def test_constant_bank_is_shared_between_contexts(ctx):
+    """The packed controller of a split rollout lives in ONE constant bank per device: two contexts (two streams) that
+    alternate between different controllers must each see their own."""
+    from clr_b200 import runtime, workloads
+    other = runtime.Context(0)
+    try:
+        uni = load_net("Unicycle")
+        alt = _synthetic_net([4, 60, 2], ["ReLU", "Id"], 77)
+        x0, Wd = workloads.unicycle_samples(np.random.default_rng(9), 700, 6)
+        refs = [_oracle().rollout(_oracle().Net(n.as_tuples()), "Unicycle", 4, 1, 2, x0, Wd, 0.0, 0.2, 1.2, 6, post=p)
+                for n, p in ((uni, ("shift", -20.0)), (alt, None))]
+        du, da = ctx.upload(uni), other.upload(alt)
+        for _ in range(3):
+            a = ctx.rollout(du, "Unicycle", x0, Wd, 0.0, 0.2, 1.2, 6, post=("shift", -20.0))
+            b = other.rollout(da, "Unicycle", x0, Wd, 0.0, 0.2, 1.2, 6)
+            np.testing.assert_allclose(a["X_end"], refs[0]["X_end"], rtol=0, atol=TRAJ_ATOL)
+            np.testing.assert_allclose(b["X_end"], refs[1]["X_end"], rtol=0, atol=TRAJ_ATOL)
+            np.testing.assert_allclose(b["U"], refs[1]["U"], rtol=0, atol=TRAJ_ATOL)
+    finally:
+        other.close()
+
+
+def test_split_rollout_equals_fused_kernel(ctx, monkeypatch):
+    """One controller launch + one plant launch per period (the default for narrow controllers) against the fused
+    rollout_blocked_kernel (CLR_B200_RO_SPLIT=0): the same arithmetic per trajectory, so the same bits."""
+    from clr_b200 import runtime, workloads
+    net = load_net("Unicycle")
+    x0, Wd = workloads.unicycle_samples(np.random.default_rng(31), 5000, 12)
+    monkeypatch.setenv("CLR_B200_RO_SPLIT", "0")
+    fused_ctx = runtime.Context(0)
+    monkeypatch.delenv("CLR_B200_RO_SPLIT")
+    try:
+        for alg in ("Tsit5", "RK4"):
+            a = ctx.rollout(ctx.upload(net), "Unicycle", x0, Wd, 0.0, 0.2, 2.3, 12, alg=alg, post=("shift", -20.0))
+            b = fused_ctx.rollout(fused_ctx.upload(net), "Unicycle", x0, Wd, 0.0, 0.2, 2.3, 12, alg=alg, post=("shift", -20.0))
+            assert np.array_equal(a["X_end"], b["X_end"]) and np.array_equal(a["U"], b["U"])
+            assert np.array_equal(a["naccept"], b["naccept"]) and np.array_equal(a["nreject"], b["nreject"])
+    finally:
+        fused_ctx.close()
