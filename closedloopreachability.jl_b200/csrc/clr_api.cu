@@ -124,6 +124,7 @@ struct clr_ctx {
     int wide_mode = 0;                   // CLR_B200_WIDE=1: the several-threads-per-neuron relaxation in the lean kernel too (experiments)
     bool debug = false;                  // CLR_B200_DEBUG: one line per DeepZ launch on stderr
     int tiny = 1;                        // clr_set_tiny: narrow networks take the one-warp-per-cell kernel
+    int reduce_reg = 1;                  // CLR_B200_REDUCE_REG=0: the order reduction with the shared-memory sort for every width (A/B, tests)
     int ro_split = 1;                    // CLR_B200_RO_SPLIT=0: narrow controllers stay in the fused rollout kernel (experiments)
     // optional per-pass timing of the last DeepZ call (clr_set_profiling)
     int profiling = 0;
@@ -906,6 +907,7 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* wv = getenv("CLR_B200_WIDE")) c->wide_mode = atoi(wv) != 0;
     c->debug = getenv("CLR_B200_DEBUG") != nullptr;
+    if (const char* v = getenv("CLR_B200_REDUCE_REG")) c->reduce_reg = atoi(v) != 0;
     if (const char* v = getenv("CLR_B200_RO_SPLIT")) c->ro_split = atoi(v) != 0;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state, sizeof(DevCallState));
@@ -1293,15 +1295,27 @@ int32_t clr_deepz_fetch_reduced(clr_ctx* ctx, int32_t order, double* out_c, doub
     }
     int cap2 = 1;                       // the index array is sorted over the next power of two
     while (cap2 < A.cap) cap2 <<= 1;
-    const size_t smem = (size_t)RD_WARPS * ((size_t)A.cap * sizeof(double) + (size_t)cap2 * sizeof(int));
     A.cap2 = cap2;
-    if (smem > (size_t)ctx->smem_optin) return fail(ctx, CLR_ERR_CAPACITY, "keep_cap = %d is too large for the order reduction", A.cap);
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(reduce_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
     const long long want = ((long long)N + RD_WARPS - 1) / RD_WARPS;
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)ctx->smem_optin / (smem + 1024)));
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sms * per_sm));
-    reduce_order_kernel<<<grid, RD_WARPS * 32, smem, ctx->stream>>>(A);
+    // zonotopes of at most 256 generators whose staged copy fits: generators staged in shared memory, sort in registers
+    const int E = std::max(1, cap2 / 32);
+    const size_t smem_reg = (size_t)RD_WARPS * (2 * (size_t)A.cap * m * sizeof(double) + (size_t)32 * E * sizeof(int));
+    if (E <= 8 && smem_reg <= (size_t)ctx->smem_optin / 2 && ctx->reduce_reg) {
+        void (*kern)(ReduceArgs) = E == 1 ? reduce_order_reg_kernel<1> : E == 2 ? reduce_order_reg_kernel<2>
+                                 : E == 4 ? reduce_order_reg_kernel<4> : reduce_order_reg_kernel<8>;
+        if (smem_reg > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)ctx->smem_optin / (smem_reg + 1024)));
+        const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sms * per_sm));
+        kern<<<grid, RD_WARPS * 32, smem_reg, ctx->stream>>>(A);
+    } else {
+        const size_t smem = (size_t)RD_WARPS * ((size_t)A.cap * sizeof(double) + (size_t)cap2 * sizeof(int));
+        if (smem > (size_t)ctx->smem_optin) return fail(ctx, CLR_ERR_CAPACITY, "keep_cap = %d is too large for the order reduction", A.cap);
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(reduce_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)ctx->smem_optin / (smem + 1024)));
+        const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sms * per_sm));
+        reduce_order_kernel<<<grid, RD_WARPS * 32, smem, ctx->stream>>>(A);
+    }
     CU(cudaGetLastError());
     ctx->launches++;
     int err = 0;

@@ -98,3 +98,115 @@ __global__ void __launch_bounds__(RD_WARPS * 32) reduce_order_kernel(ReduceArgs 
         __syncwarp();
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// The same reduction for zonotopes of at most 32 E generators (E = 1, 2, 4, 8: every controller of the reference's models),
+// restructured around what the profile of the kernel above showed (round 2: 64 % of the samples in the interval-hull loop --
+// m of 32 lanes chasing gathers that miss L1 -- and 28 % in the shared-memory sort):
+//   * a cell's generators are read from HBM ONCE, coalesced, into the warp's shared-memory slice;
+//   * the (weight, index) pairs are sorted in REGISTERS: element e = 32 r + lane sits in register r of its lane, the bitonic
+//     network exchanges through warp shuffles (distance < 32) or between registers (distance >= 32); the key is the weight's
+//     bit pattern (weights are >= +0, so the integer order is the floating-point order), ties by index = the stable order;
+//   * the generators to be boxed are gathered into sorted order by all 32 lanes first, so that the m sequential row sums
+//     (the reference's summation order) read consecutive shared-memory words instead of chasing indices.
+// Same results bit for bit as reduce_order_kernel and the oracle's twin.
+// ---------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(RD_WARPS * 32) reduce_order_reg_kernel(ReduceArgs A) {
+    extern __shared__ __align__(16) unsigned char rd_smem[];
+    // warp-uniform values go through a lane-0 broadcast: ptxas then knows that the branches on them do not diverge and emits the
+    // sort's shuffles without a WARPSYNC / convergence-barrier pair around each of them
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int m = A.m, kept = m * (A.order - 1), gout = m * A.order;
+    const size_t slice = (size_t)A.cap * m;
+    double* gs = reinterpret_cast<double*>(rd_smem) + (size_t)warp * 2 * slice;      // the cell's generators as stored
+    double* hs = gs + slice;                                                         // |.| of the boxed ones, in sorted order
+    int* sorted = reinterpret_cast<int*>(rd_smem + sizeof(double) * (size_t)RD_WARPS * 2 * slice) + (size_t)warp * 32 * E;
+    for (long long cell = (long long)blockIdx.x * RD_WARPS + warp; cell < A.N; cell += (long long)gridDim.x * RD_WARPS) {
+        const int p = __shfl_sync(0xffffffffu, A.keepN[cell], 0);
+        const double* G = A.keepG + (size_t)cell * slice;
+        double* oG = A.outG + (size_t)cell * gout * m;
+        for (int i = lane; i < m; i += 32) A.outC[cell * m + i] = A.keepC[cell * m + i];
+        if (p < kept) {                      // the reference indexes past the end here (BoundsError)
+            if (lane == 0) atomicExch(A.error, 1);
+            continue;
+        }
+        __syncwarp();                        // the previous cell's shared-memory reads are done
+        for (int t = lane; t < p * m; t += 32) gs[t] = G[t];
+        __syncwarp();
+        if (kept > 0) {
+            long long key[E];
+            int idx[E];
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                const int j = r * 32 + lane;
+                idx[r] = j;
+                key[r] = -1;                 // padding sorts behind every generator
+                if (j < p) {
+                    double s = 0.0, mx = 0.0;
+                    for (int i = 0; i < m; i++) { const double a = fabs(gs[j * m + i]); s += a; mx = fmax(mx, a); }
+                    key[r] = __double_as_longlong(s - mx);
+                }
+            }
+            constexpr int n2 = 32 * E;
+#pragma unroll
+            for (int k = 2; k <= n2; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (j >= 32) {
+                        const int rj = j >> 5;
+#pragma unroll
+                        for (int r = 0; r < E; r++) {
+                            if ((r & rj) == 0) {
+                                const int r2 = r | rj;
+                                const bool up = (((r * 32 + lane) & k) == 0);
+                                const bool a_first = key[r] > key[r2] || (key[r] == key[r2] && idx[r] < idx[r2]);
+                                if (a_first != up) {
+                                    const long long tk = key[r]; key[r] = key[r2]; key[r2] = tk;
+                                    const int ti = idx[r]; idx[r] = idx[r2]; idx[r2] = ti;
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < E; r++) {
+                            const long long ok = __shfl_xor_sync(0xffffffffu, key[r], j);
+                            const int oi = __shfl_xor_sync(0xffffffffu, idx[r], j);
+                            const bool up = (((r * 32 + lane) & k) == 0), lower = (lane & j) == 0;
+                            const bool mine_first = key[r] > ok || (key[r] == ok && idx[r] < oi);
+                            if (mine_first != (lower == up)) { key[r] = ok; idx[r] = oi; }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < E; r++) sorted[r * 32 + lane] = idx[r];
+            __syncwarp();
+        }
+        // kept generators, in sorted order
+        for (int t = lane; t < kept * m; t += 32) {
+            const int k = t / m, i = t - k * m;
+            oG[t] = gs[sorted[k] * m + i];
+        }
+        // the others, gathered into sorted order by all lanes ...
+        const int nb = p - kept;
+        for (int t = lane; t < nb * m; t += 32) {
+            const int k = t / m, i = t - k * m;
+            hs[t] = fabs(gs[(kept > 0 ? sorted[kept + k] : k) * m + i]);
+        }
+        __syncwarp();
+        // ... and their interval hull: lane i owns row i, sequential sums in sorted order (8 loads in flight)
+        for (int i = lane; i < m; i += 32) {
+            double d = 0.0;
+            for (int k0 = 0; k0 < nb; k0 += 8) {
+                double t[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) t[q] = k0 + q < nb ? hs[(k0 + q) * m + i] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) d += t[q];             // + 0.0 past the end: exact
+            }
+            for (int i2 = 0; i2 < m; i2++) oG[(size_t)(kept + i2) * m + i] = 0.0;
+            oG[(size_t)(kept + i) * m + i] = d;
+        }
+    }
+}

@@ -484,6 +484,27 @@ def test_order2_reduction_of_kept_zonotopes(ctx):
     np.testing.assert_allclose(red["G"], refG, rtol=0, atol=1e-12 * scale)
 
 
+@pytest.mark.parametrize("name,lo,hi,parts,cap", [
+    ("TORA_ReLU", [0.6, -0.7, -0.4, 0.5], [0.7, -0.6, -0.3, 0.6], [3, 3, 2, 2], 24),      # 32-slot sort: one key per lane
+    ("TORA_ReLU", [0.6, -0.7, -0.4, 0.5], [0.7, -0.6, -0.3, 0.6], [3, 3, 2, 2], 40),      # two keys per lane
+    ("TORA_sigmoid", [0.6, -0.7, -0.4, 0.5], [0.7, -0.6, -0.3, 0.6], [3, 2, 2, 2], 100),  # four keys per lane, 64 generators
+    ("Quadrotor", [-0.004] * 6 + [0.0] * 6, [0.004] * 6 + [0.0] * 6, [2, 2, 1, 1, 1, 1] + [1] * 6, 300)])   # 512 slots: the shared-memory sort
+def test_order_reduction_every_sort_width(ctx, name, lo, hi, parts, cap):
+    """clr_deepz_fetch_reduced picks its kernel by the generator capacity (keys sorted in registers up to 256 slots, in shared
+    memory beyond): every width against the oracle's twin on the same zonotopes, bit for bit."""
+    import clr_b200
+    net = load_net(name)
+    g = clr_b200.split_box(lo, hi, parts)
+    got = ctx.deepz_boxgrid(ctx.upload(net), g.partition, g.centers, g.radii, keep_cap=cap)
+    N, m = got["lo"].shape
+    for order in (1, 2, 3):
+        if got["ncols"].min() < m * (order - 1):
+            continue
+        red = ctx.fetch_reduced(N, m, order)
+        oc, oG = _oracle().reduce_order(got["ncols"], got["c"], got["G"], order)
+        assert np.array_equal(red["c"], oc) and np.array_equal(red["G"], oG)
+
+
 def test_order_reduction_errors(ctx):
     net = load_net("Quadrotor")
     dn = ctx.upload(net)
