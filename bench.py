@@ -430,7 +430,28 @@ def run_ours(args):
                         "frac_of_fp64_fma_peak": flops / (ms * 1e-3) / 1e12 / DFMA_PEAK_TFLOPS}
         line["secondary"] = {"metric": "sim trajectories/sec", "config": f"Unicycle, {N} trajectories per GPU x {iters} "
                              "control periods, 4->500->2 ReLU controller; Tsit5 = the reference's solver, RK4 = 4 fixed steps / period",
+                             "kernels": "per control period one controller_cw_kernel launch (packed controller in the constant bank, "
+                                        "weights in uniform registers) + one rollout_ode_kernel launch",
                              **res}
+        # end to end through the host-buffer call (x0 / disturbances up, X_end / U back, blocking) on a bounded sample, and
+        # the CPU restatement (OpenMP over trajectories) on the host cores next to it -- rank 0, one GPU only
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            ns = min(N, 100000)
+            t0 = time.perf_counter()
+            ctx.rollout(du, "Unicycle", x0[:ns], Wd[:, :ns], 0.0, 0.2, 10.0, iters, post=("shift", -20.0), counts=False)
+            t1 = time.perf_counter()
+            ctx.rollout(du, "Unicycle", x0[:ns], Wd[:, :ns], 0.0, 0.2, 10.0, iters, post=("shift", -20.0), counts=False)
+            t2 = time.perf_counter()
+            line["secondary"]["e2e"] = {"value": ns / min(t1 - t0, t2 - t1), "unit": "trajectories/s", "sample": f"{ns} trajectories",
+                                        "h2d_bytes": int(8 * ns * (4 + iters)), "d2h_bytes": int(8 * ns * iters * 6)}
+            from oracle import cbind
+            nc = min(N, 20000)
+            on = cbind.Net(uni.as_tuples())
+            t0 = time.perf_counter()
+            cbind.rollout(on, "Unicycle", 4, 1, 2, x0[:nc], Wd[:, :nc], 0.0, 0.2, 10.0, iters, post=("shift", -20.0))
+            dt = time.perf_counter() - t0
+            line["secondary"]["cpu_baseline"] = {"value": nc / dt, "unit": "trajectories/s", "cores": cbind.num_threads(),
+                                                 "kind": "port", "sample": f"{nc} trajectories x {iters} periods, Tsit5"}
     if rank == 0:
         emit(line)
     ctx.close()

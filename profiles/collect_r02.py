@@ -17,8 +17,10 @@ pairs = {"f2_bench.json": "bench_n1.json", "f2_bench_ref.json": "bench_reference
          "f2_latency.txt": "latency_small_b200.txt", "f2_reduce.txt": "reduce_bench_b200.txt",
          "f2_project.txt": "project_bench_b200.txt", "f2_shards.txt": "shard_costs_b200.txt",
          "f2_ncu_quad.json": "ncu_deepz_c3_quadrotor.json", "f2_ncu_quad_lines.txt": "ncu_deepz_c3_quadrotor_lines.txt",
-         "f2_ncu_rollout.json": "ncu_rollout_launch.json", "f2_ncu_rollout_lines.txt": "ncu_rollout_launch_lines.txt",
-         "f2_ncu_reduce.json": "ncu_reduce_launch.json", "f2_ncu_reduce_lines.txt": "ncu_reduce_launch_lines.txt",
+         "f2_ncu_controller_cw.json": "ncu_controller_cw.json", "f2_ncu_controller_cw_lines.txt": "ncu_controller_cw_lines.txt",
+         "f2_ncu_rollout_ode.json": "ncu_rollout_ode.json", "f2_ncu_rollout_ode_lines.txt": "ncu_rollout_ode_lines.txt",
+         "f2_latency_c.txt": "latency_c_abi_b200.txt", "f2_plain_rollout.log": "rollout_bench_b200.txt",
+         "f2_ncu_reduce.json": "ncu_reduce_reg_launch.json", "f2_ncu_reduce_lines.txt": "ncu_reduce_reg_launch_lines.txt",
          "f2_ncu_wide.json": "ncu_deepz_wide_pass.json", "f2_ncu_wide_lines.txt": "ncu_deepz_wide_pass_lines.txt",
          "f2_pytest.log": "pytest_gpu.log", "f2_bench_n2.json": "bench_n2.json", "f2_bench_n4.json": "bench_n4.json",
          "f2_bench_n8.json": "bench_n8.json"}
@@ -68,7 +70,7 @@ for k, v in d.get("regimes", {}).items():
 print("peak", d["roofline"]["peak"], "cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], "clocks", d["clocks"],
       "launches", d["gpu_launches"])
 print({k: (round(v["value"] / 1e6, 2), round(v["ms"], 2), round(v["frac_of_fp64_fma_peak"], 3))
-       for k, v in d["secondary"].items() if isinstance(v, dict)})
+       for k, v in d["secondary"].items() if isinstance(v, dict) and "ms" in v})
 for r in ("stable", "mixed", "dense"):
     f = os.path.join(G, f"f2_ncu_deepz_{r}.json")
     if os.path.exists(f):
