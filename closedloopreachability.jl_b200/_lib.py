@@ -16,7 +16,7 @@ MAX_LAYERS = 32
 # every symbol include/clr_b200.h declares (tests check the export list against the header)
 SYMBOLS = [
     "clr_create", "clr_destroy", "clr_last_error", "clr_stream", "clr_synchronize", "clr_launch_count",
-    "clr_device_alloc", "clr_device_free", "clr_memcpy_h2d", "clr_memcpy_d2h", "clr_set_tile_cells",
+    "clr_device_alloc", "clr_device_free", "clr_memcpy_h2d", "clr_memcpy_d2h", "clr_host_register", "clr_host_unregister", "clr_set_tile_cells",
     "clr_set_profiling", "clr_last_pass_info", "clr_set_reorder", "clr_measure_fp64_peak", "clr_last_device_error", "clr_set_tiny",
     "clr_net_upload", "clr_net_free", "clr_deepz_boxgrid", "clr_deepz_boxgrid_cyclic", "clr_deepz_zonotopes", "clr_deepz_zonotopes_padded",
     "clr_deepz_fetch_zonotopes", "clr_deepz_fetch_reduced", "clr_project_oa", "clr_forward_points", "clr_rollout",
@@ -71,6 +71,10 @@ def lib():
     L.clr_memcpy_h2d.restype = i32
     L.clr_memcpy_d2h.argtypes = [vp, vp, vp, i64]
     L.clr_memcpy_d2h.restype = i32
+    L.clr_host_register.argtypes = [vp, vp, i64]
+    L.clr_host_register.restype = i32
+    L.clr_host_unregister.argtypes = [vp, vp]
+    L.clr_host_unregister.restype = i32
     L.clr_set_tile_cells.argtypes = [vp, i32]
     L.clr_set_tile_cells.restype = i32
     L.clr_set_reorder.argtypes = [vp, i32]

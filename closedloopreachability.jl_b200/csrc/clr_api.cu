@@ -995,6 +995,24 @@ int32_t clr_memcpy_d2h(clr_ctx* ctx, void* dst, const void* src, int64_t bytes) 
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+int32_t clr_host_register(clr_ctx* ctx, void* p, int64_t bytes) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (!p || bytes <= 0) return fail(ctx, CLR_ERR_ARG, "clr_host_register: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, CLR_ERR_CUDA, "cudaHostRegister(%lld bytes): %s", (long long)bytes, cudaGetErrorString(e)); }
+    return 0;
+}
+int32_t clr_host_unregister(clr_ctx* ctx, void* p) {
+    if (!ctx) return CLR_ERR_ARG;
+    if (!p) return 0;
+    CU(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostUnregister(p);
+    if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, CLR_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+    return 0;
+}
 int32_t clr_last_device_error(clr_ctx* ctx, int32_t* code) {
     if (!ctx || !code) return CLR_ERR_ARG;
     CU(cudaSetDevice(ctx->device));

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(RD_WARPS * 32) reduce_order_kernel(ReduceArgs 
 //     bit pattern (weights are >= +0, so the integer order is the floating-point order), ties by index = the stable order;
 //   * the generators to be boxed are gathered into sorted order by all 32 lanes first, so that the m sequential row sums
 //     (the reference's summation order) read consecutive shared-memory words instead of chasing indices.
-// Same results bit for bit as reduce_order_kernel and the oracle's twin.
+// Same results bit for bit as reduce_order_kernel (and as its CPU restatement in the tests).
 // ---------------------------------------------------------------------------------------------
 template <int E>
 __global__ void __launch_bounds__(RD_WARPS * 32) reduce_order_reg_kernel(ReduceArgs A) {

@@ -205,6 +205,13 @@ class Context:
         self._check(self.L.clr_last_pass_info(self.h, ms, C.byref(retried), C.byref(big)))
         return {"pass_ms": list(ms), "retried": retried.value, "big": big.value}
 
+    def host_register(self, a: np.ndarray) -> None:
+        """Page-lock a NumPy array in place (clr_host_register): results are then written into it by one DMA."""
+        self._check(self.L.clr_host_register(self.h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def host_unregister(self, a: np.ndarray) -> None:
+        self._check(self.L.clr_host_unregister(self.h, a.ctypes.data_as(C.c_void_p)))
+
     def last_device_error(self) -> int:
         """Device-side status word of the last CLR_FLAG_DEVICE_IO call, after synchronising (clr_last_device_error)."""
         out = C.c_int32()

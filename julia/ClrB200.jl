@@ -349,6 +349,12 @@ memcpy_h2d(ctx::Context, dst::Ptr{Cvoid}, src::Array) =
     GC.@preserve src check(ctx, ccall((:clr_memcpy_h2d, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), ctx.h, dst, pointer(src), sizeof(src)))
 memcpy_d2h(ctx::Context, dst::Array, src::Ptr{Cvoid}) =
     GC.@preserve dst check(ctx, ccall((:clr_memcpy_d2h, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), ctx.h, pointer(dst), src, sizeof(dst)))
+# Page-lock a Julia array in place (cudaHostRegister): results are then written into it by one DMA at PCIe speed instead of going
+# through the context's pinned staging buffers.  Register once per buffer, unregister before the array can be collected.
+host_register(ctx::Context, a::Array) =
+    GC.@preserve a check(ctx, ccall((:clr_host_register, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), ctx.h, pointer(a), sizeof(a)))
+host_unregister(ctx::Context, a::Array) =
+    GC.@preserve a check(ctx, ccall((:clr_host_unregister, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, pointer(a)))
 
 # ---- several GPUs behind one handle (clr_create_multi) ------------------------------------------------------------
 mutable struct MultiContext

@@ -250,3 +250,25 @@ def test_split_rollout_equals_fused_kernel(ctx, monkeypatch):
             assert np.array_equal(a["naccept"], b["naccept"]) and np.array_equal(a["nreject"], b["nreject"])
     finally:
         fused_ctx.close()
+
+
+def test_pageable_and_registered_host_buffers_agree(ctx):
+    """Host buffers may be pageable (the driver stages the copy) or page-locked in place (clr_host_register: one DMA): the same
+    bytes either way; registering twice / unregistering twice is harmless."""
+    from clr_b200 import workloads
+    net = load_net("Unicycle")
+    dn = ctx.upload(net)
+    N, iters = 70001, 9
+    x0, Wd = workloads.unicycle_samples(np.random.default_rng(17), N, iters)
+    a = ctx.rollout(dn, "Unicycle", x0, Wd, 0.0, 0.2, 1.8, iters, post=("shift", -20.0))
+    ctx.host_register(x0); ctx.host_register(Wd); ctx.host_register(x0)
+    try:
+        b = ctx.rollout(dn, "Unicycle", x0, Wd, 0.0, 0.2, 1.8, iters, post=("shift", -20.0))
+    finally:
+        ctx.host_unregister(x0); ctx.host_unregister(Wd)
+    ctx.host_unregister(x0)                               # idempotent
+    assert np.array_equal(a["X_end"], b["X_end"]) and np.array_equal(a["U"], b["U"]) and np.array_equal(a["naccept"], b["naccept"])
+    idx = np.arange(0, N, 997)
+    ref = _oracle().rollout(_oracle().Net(net.as_tuples()), "Unicycle", 4, 1, 2, x0[idx], Wd[:, idx], 0.0, 0.2, 1.8, iters,
+                            post=("shift", -20.0))
+    np.testing.assert_allclose(a["X_end"][:, idx], ref["X_end"], rtol=0, atol=TRAJ_ATOL)
