@@ -1067,16 +1067,14 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                 // W x for every used column, in place: rows 0 .. mt-1 of the column become its image (a thread per column, k
                 // ascending; rows >= kAct of the store are zero).  The fused layer has at most 4 rows: the scalar control of most
                 // models, or the folded post-processing.
-                const int kA = min(nt, S.kAct);
-                for (int col = tid; col < nCols; col += NT) {
-                    int lo_ = 0, hi_ = nCells;                 // cell of this column: the last ci with colOff[ci] <= col
-                    while (hi_ - lo_ > 1) { const int mid = (lo_ + hi_) >> 1; if (colOff[mid] <= col) lo_ = mid; else hi_ = mid; }
-                    const int j = col - colOff[lo_];
-                    if (j >= S.wUsed[flip][lo_]) continue;
-                    double* x = cur + col * P;
-                    double yv[4];
-                    if (nt <= 4) {
-                        double xv[4];
+                if (nt <= 4) {
+                    for (int col = tid; col < nCols; col += NT) {
+                        int lo_ = 0, hi_ = nCells;                 // cell of this column: the last ci with colOff[ci] <= col
+                        while (hi_ - lo_ > 1) { const int mid = (lo_ + hi_) >> 1; if (colOff[mid] <= col) lo_ = mid; else hi_ = mid; }
+                        const int j = col - colOff[lo_];
+                        if (j >= S.wUsed[flip][lo_]) continue;
+                        double* x = cur + col * P;
+                        double xv[4], yv[4];
 #pragma unroll
                         for (int k = 0; k < 4; k++) xv[k] = k < nt ? x[k] : 0.0;
 #pragma unroll
@@ -1086,18 +1084,38 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                             for (int k = 0; k < 4; k++) if (k < nt && r < mt) sacc += __ldg(Lt.Wcm + (size_t)k * mt + r) * xv[k];
                             yv[r] = sacc;
                         }
-                    } else {
 #pragma unroll
-                        for (int r = 0; r < 4; r++) yv[r] = 0.0;
-#pragma unroll 4
-                        for (int k = 0; k < kA; k++) {
-                            const double xk = x[k];
-#pragma unroll
-                            for (int r = 0; r < 4; r++) if (r < mt) yv[r] += __ldg(Lt.Wcm + (size_t)k * mt + r) * xk;
+                        for (int r = 0; r < 4; r++) if (r < mt) x[r] = j == 0 ? yv[r] + __ldg(Lt.bias + r) : yv[r];
+                    }
+                } else {
+                    // A real layer (e.g. 100 -> 1, 64 -> 3): on the tensor pipe, like every other product, but without the
+                    // product / relaxation / layout cycle -- a warp owns whole column blocks (8 columns), multiplies them by the
+                    // layer's single row block (fragments from L2, B fragments conflict-free from the store: a thread per column
+                    // walking its column hits an 8-way bank conflict at P = 100 or 68) and overwrites rows 0 .. mt-1 of ITS columns:
+                    // no barrier.  Two blocks per warp and round for two independent DMMA chains.  The bias of the centre
+                    // columns is added behind the barrier below.
+                    const int ksE = min(Lt.ksteps, (S.kAct + 3) >> 2);
+                    const double* Af = Lt.Afrag + lane;
+                    const int qr = lane >> 2, qc = lane & 3;
+                    const int nblk = (nCols + 7) >> 3;
+                    for (int b0 = warp * 2; b0 < nblk; b0 += nWarps * 2) {
+                        const bool two = b0 + 1 < nblk;
+                        const double* x0 = cur + (b0 * 8 + qr) * P + qc;
+                        const double* x1 = two ? x0 + 8 * P : x0;
+                        double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
+                        for (int k = 0; k < ksE; k++) {
+                            const double av = __ldg(Af + k * 32);
+                            dmma884(d00, d01, av, x0[k * 4]);
+                            dmma884(d10, d11, av, x1[k * 4]);
+                        }
+                        if (qr < mt) {
+                            const int c0 = b0 * 8 + qc * 2;
+                            if (c0 < nCols) cur[c0 * P + qr] = d00;
+                            if (c0 + 1 < nCols) cur[(c0 + 1) * P + qr] = d01;
+                            if (two && c0 + 8 < nCols) cur[(c0 + 8) * P + qr] = d10;
+                            if (two && c0 + 9 < nCols) cur[(c0 + 9) * P + qr] = d11;
                         }
                     }
-#pragma unroll
-                    for (int r = 0; r < 4; r++) if (r < mt) x[r] = j == 0 ? yv[r] + __ldg(Lt.bias + r) : yv[r];
                 }
                 // images mu_i W[:, i] of the generators appended by the last relaxation, item-major in the 8 slack columns
                 // behind the layout (when the tile's list fits; otherwise the output loops walk the row masks)
@@ -1109,6 +1127,13 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                     }
                 }
                 __syncthreads();
+                if (nt > 4) {
+                    for (int t = tid; t < nCells * mt; t += NT) {
+                        const int ci = t / mt, r = t - ci * mt;
+                        cur[colOff[ci] * P + r] += __ldg(Lt.bias + r);
+                    }
+                    __syncthreads();
+                }
             }
             // ranks of the surviving output generators (remove_zero_columns); the position table is free now
             unsigned short* colRank = colPosT;
