@@ -100,8 +100,10 @@ struct clr_ctx {
     size_t io_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // small-call path of the blocking mode: one pinned bounce buffer and its device twin; the inputs of a call (and
     // the hull seed) go up in ONE copy, the boxes and the hull come back in ONE copy
-    unsigned char* h_bounce = nullptr;   // pinned
+    unsigned char* h_bounce = nullptr;   // pinned, mapped: m_bounce is its address as the device sees it
     unsigned char* d_bounce = nullptr;
+    unsigned char* m_bounce = nullptr;
+    int zero_copy = 1;                   // CLR_B200_ZEROCOPY=0: small calls of narrow networks copy their inputs / results like every other call
     size_t bounce_used = 0, bounce_flushed = 0;
     bool bounce_open = false;
     double* d_hull = nullptr;            // 2 * m_out
@@ -665,6 +667,16 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     // come back in one copy from one contiguous region [hull | lo | hi] of the bounce buffer.
     size_t fast_off = 0, fast_bytes = 0;
     bool fast = false;
+    // Narrow networks (every layer at most 32 neurons wide: ACC, VerticalCAS, InvertedPendulum ...) without statistics or kept
+    // zonotopes take the one-small-CTA-per-cell kernel (tiny.cuh): the tiled DMMA kernel's phases are a ~40 us latency chain there.
+    const bool kstats_early = want_stats || keep_cap > 0;
+    const size_t smem_cta_early = ((size_t)ctx->smem_optin + 1024) / DZ_CTAS - 1024;
+    bool tiny = !kstats_early && keep_cap == 0 && ctx->tile_cells == 0 && ctx->tiny && D.n_in <= TN_ROWS;
+    for (int l = 0; l < D.L && tiny; l++) tiny = D.layer[l].m <= TN_ROWS && D.layer[l].n <= TN_ROWS;
+    const int tiny_cols = worst_cols(D, p0max) + 1;
+    const size_t tsm = ((size_t)tiny_cols + TN_WARPS) * TN_ROWS * sizeof(double);      // the cell's store + the partial radius sums
+    tiny = tiny && tsm <= smem_cta_early;
+    bool zc = false;      // zero copy: the kernel reads its inputs from and writes its boxes to the pinned bounce buffer itself
     // The scheduler state travels the same way: its zeroed image goes up with the inputs (no memset call) and comes back with
     // the results (no copy of its own): one region [state | hull | lo | hi] -- four driver calls per step in all.
     const size_t sb = (sizeof(DevCallState) + 255) & ~(size_t)255;
@@ -685,6 +697,24 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
             if (want_hull) { out.hull_lo = dbase; out.hull_hi = dbase + m; }
             if (ob) { out.out_lo = dbase + 2 * (want_hull ? m : 0); out.out_hi = out.out_lo + (size_t)m * N; }
         }
+    }
+    // The reference's own problem sizes on narrow networks (ONE zonotope per control step for ACC): the call is three copies and a
+    // 15 us kernel.  The pinned bounce buffer is mapped into the device's address space, so the kernel reads the staged inputs from
+    // it and writes the boxes into it over PCIe itself -- no H2D, no D2H: one launch and one synchronisation.  The hull is the
+    // min / max of the boxes, taken on the host; the only state the tiny kernel touches is the error word.
+    zc = tiny && fast && ctx->zero_copy && ctx->m_bounce && out_lo && out_hi && N <= 8192;
+    if (zc) {
+        auto remap = [&](const void* p) -> const void* {
+            const unsigned char* b = (const unsigned char*)p;
+            return (p && b >= ctx->d_bounce && b < ctx->d_bounce + CLR_BOUNCE_BYTES) ? ctx->m_bounce + (b - ctx->d_bounce) : p;
+        };
+        in.centers = (const double*)remap(in.centers); in.radii = (const double*)remap(in.radii);
+        in.C = (const double*)remap(in.C); in.G = (const double*)remap(in.G);
+        in.col_off = (const long long*)remap(in.col_off); in.ncols = (const int*)remap(in.ncols);
+        out.out_lo = (double*)remap(out.out_lo); out.out_hi = (double*)remap(out.out_hi);
+        out.hull_lo = nullptr; out.hull_hi = nullptr;
+        ctx->d_state = (DevCallState*)(ctx->m_bounce + fast_off);
+        ctx->bounce_flushed = ctx->bounce_used;          // nothing goes up
     }
     { int rcf = bounce_flush(ctx); if (rcf) return rcf; }
     ctx->bounce_open = false;
@@ -754,13 +784,6 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     sp.pass = 0;
     ctx->pass_ms[0] = ctx->pass_ms[1] = ctx->pass_ms[2] = 0.f;
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    // Narrow networks (every layer at most 32 neurons wide: ACC, VerticalCAS, InvertedPendulum ...) without statistics or kept
-    // zonotopes take the one-small-CTA-per-cell kernel (tiny.cuh): the tiled DMMA kernel's phases are a ~40 us latency chain there.
-    bool tiny = !kstats && keep_cap == 0 && ctx->tile_cells == 0 && ctx->tiny && D.n_in <= TN_ROWS;
-    for (int l = 0; l < D.L && tiny; l++) tiny = D.layer[l].m <= TN_ROWS && D.layer[l].n <= TN_ROWS;
-    const int tiny_cols = worst_cols(D, p0max) + 1;
-    const size_t tsm = ((size_t)tiny_cols + TN_WARPS) * TN_ROWS * sizeof(double);      // the cell's store + the partial radius sums
-    tiny = tiny && tsm <= smem_total;
     if (tiny) {
         if (tsm > 48 * 1024) CU(cudaFuncSetAttribute(deepz_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
         const long long per_sm = std::max<long long>(1, std::min<long long>(8, (long long)(smem_total / (tsm + 1024))));
@@ -772,7 +795,17 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
     if (ctx->profiling) CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     sp.pass = 1;
     bool fast_done = false;
-    if (fast) {
+    if (zc) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        memcpy(ctx->h_state, ctx->h_bounce + fast_off, sizeof(DevCallState));
+        fast_done = true;
+        if (want_hull) {                                    // min / max of the boxes (what the device-side hull holds)
+            double* hb = (double*)(ctx->h_bounce + fast_off + sb);
+            const double* lo = hb + 2 * m; const double* hi = lo + (size_t)m * N;
+            for (long long j = 0; j < N; j++)
+                for (int i = 0; i < m; i++) { hb[i] = fmin(hb[i], lo[j * m + i]); hb[m + i] = fmax(hb[m + i], hi[j * m + i]); }
+        }
+    } else if (fast) {
         // one round trip: scheduler state and results together; the retry pass only runs when a tile overflowed
         CU(cudaMemcpyAsync(ctx->h_bounce + fast_off, ctx->d_bounce + fast_off, fast_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -780,7 +813,7 @@ int run_deepz(clr_ctx* ctx, clr_net* net, Compiled* c, DeepzInput& in, int p0max
         memcpy(ctx->h_state, ctx->h_bounce + fast_off, sizeof(DevCallState));
         fast_done = ctx->h_state->n_retry == 0 && ctx->h_state->n_big == 0;
     }
-    if (!fast || ctx->h_state->n_retry > 0) {
+    if (!zc && (!fast || ctx->h_state->n_retry > 0)) {
         if (!tiny && (rc = launch_deepz(ctx, false, kstats, c, grid, threads, meta + (size_t)sp.cap * 8, in, out, sp))) return rc;
         if (ctx->profiling) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
         // how many cells did not fit in shared memory at all?
@@ -907,6 +940,7 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* wv = getenv("CLR_B200_WIDE")) c->wide_mode = atoi(wv) != 0;
     c->debug = getenv("CLR_B200_DEBUG") != nullptr;
+    if (const char* v = getenv("CLR_B200_ZEROCOPY")) c->zero_copy = atoi(v) != 0;
     if (const char* v = getenv("CLR_B200_REDUCE_REG")) c->reduce_reg = atoi(v) != 0;
     if (const char* v = getenv("CLR_B200_RO_SPLIT")) c->ro_split = atoi(v) != 0;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -914,7 +948,8 @@ int32_t clr_create(int32_t device, clr_ctx** out) {
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_state, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_chk, 2 * sizeof(int));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_bounce, CLR_BOUNCE_BYTES);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_bounce, CLR_BOUNCE_BYTES, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&c->m_bounce, c->h_bounce, 0);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_bounce, CLR_BOUNCE_BYTES);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_state2, sizeof(DevCallState));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_live, sizeof(int) * CLR_DEV_MAX_LAYERS * CLR_MAX_ROWS);

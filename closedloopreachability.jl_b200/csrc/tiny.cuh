@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(TN_WARPS * 32) deepz_tiny_kernel(const DevNet*
                 __syncthreads();
             }
         }
-        if (overflow) { if (threadIdx.x == 0) atomicCAS(&st->error, 0, (int)CLR_ERR_CAPACITY); continue; }
+        // (a plain store: every writer stores the same value, and on the zero-copy path of small calls the word lives in mapped host memory)
+        if (overflow) { if (threadIdx.x == 0) { *(volatile int*)&st->error = (int)CLR_ERR_CAPACITY; __threadfence_system(); } continue; }
         // ---- output box --------------------------------------------------------------------------------------------------------
         const double rad = tn_radius(X, part, w, lane, warp);
         if (warp == 0 && lane < mOut) {
