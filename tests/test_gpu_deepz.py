@@ -138,7 +138,7 @@ def test_matrix_and_projection_postprocessing(ctx, post):
     # 1e-12 relative to the zonotope's scale (largest |entry| of centre and generators): entries that are
     # sums with cancellation cannot agree element-wise-relative across equally valid summation orders
     scale = max(np.abs(ref["c"]).max(), np.abs(ref["G"]).max())
-    np.testing.assert_allclose(np.abs(got["G"]), np.abs(ref["G"]), rtol=0, atol=1e-12 * scale)
+    np.testing.assert_allclose(got["G"], ref["G"], rtol=0, atol=1e-12 * scale)          # signed
 
 
 @pytest.mark.parametrize("regime,count", [("stable", 3000), ("mixed", 600), ("dense", 160)])
@@ -430,7 +430,7 @@ def test_random_networks_fuzz(ctx):
         assert got["stats"]["sum_unstable"] == ref["stats"]["sum_unstable"], info
         assert got["stats"]["sum_p_in"] == ref["stats"]["sum_p_in"], info
         gs = max(np.abs(ref["G"]).max(), np.abs(ref["c"]).max(), 1e-300)
-        np.testing.assert_allclose(np.abs(got["G"]), np.abs(ref["G"]), rtol=0, atol=1e-12 * gs, err_msg=str(info))
+        np.testing.assert_allclose(got["G"], ref["G"], rtol=0, atol=1e-12 * gs, err_msg=str(info))       # signed
         np.testing.assert_allclose(got["c"], ref["c"], rtol=0, atol=1e-12 * gs, err_msg=str(info))
         # the same cells as a box-only call (small-call path, lean / no-statistics instantiations, post-processing applied
         # in the output stage): same boxes within the tolerance, hull = min / max of the cells
