@@ -147,7 +147,10 @@ int32_t clr_last_pass_info(clr_ctx* ctx, double* pass_ms /*3*/, int64_t* retried
 int32_t clr_measure_fp64_peak(clr_ctx* ctx, double ms, double* tflops);
 
 /* ---- networks ------------------------------------------------------------------------------ */
-/* dims has n_layers+1 entries; W[l] is dims[l+1] x dims[l] column-major, b[l] has dims[l+1] entries */
+/* dims has n_layers+1 entries; W[l] is dims[l+1] x dims[l] column-major, b[l] has dims[l+1] entries.
+   A clr_net belongs to the context it was uploaded to and is used by that context's host task only: the calls that take a
+   `const clr_net*` never change the network, but they build and cache its device images inside it (one per pre / post-processing
+   and input dimension, plus the pilot-ordered image of large box-grid calls) -- logically const, not safe to share between threads. */
 int32_t clr_net_upload(clr_ctx* ctx, int32_t n_layers, const int32_t* dims, const int32_t* act,
                        const double* const* W, const double* const* b, clr_net** out);
 void clr_net_free(clr_net* net);
