@@ -865,7 +865,11 @@ deepz_kernel(const DevNet* __restrict__ net, DeepzInput in, DeepzOutput out, Dev
                         }
                         y[0] = cn;
                         if (collapse) y[P] = la * rad;       // LazySets' one-row linear_map: a single generator
-                        else if (la == 0.0) { for (int j = 1; j < w; j++) y[j * P] = 0.0; }     // inactive row: exactly zero, no reads
+                        else if (la == 0.0) {                                                   // inactive row: exactly zero, no reads
+#pragma unroll
+                            for (int q = 0; q < 8; q++) if (q + 1 < w) y[(q + 1) * P] = 0.0;
+                            for (int j = 9; j < w; j++) y[j * P] = 0.0;
+                        }
                         else if (la != 1.0) {
 #pragma unroll
                             for (int q = 0; q < 8; q++) if (q + 1 < w) y[(q + 1) * P] = v[q] * la;
