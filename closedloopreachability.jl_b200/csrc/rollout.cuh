@@ -4,9 +4,14 @@
 // control period the controller forward(x, network) (src/simulate.jl:101-106), the extended state
 // [x; w; u] (src/simulate.jl:117-124) and the ODE solve of _solve_ensemble
 // (ext/ClosedLoopReachabilityOrdinaryDiffEqExt.jl:28-45: Tsit5() with OrdinaryDiffEq's defaults).
-// One thread owns one trajectory for the whole horizon: the state stays in registers, the network
-// weights are staged once per CTA in shared memory and read as warp-wide broadcasts, and the only
-// HBM traffic is the state/disturbance read and the X_end / U write per period.
+// Three forms of the same arithmetic per trajectory:
+//   * narrow controllers (every materialised vector has at most 8 entries, e.g. Unicycle's 4 -> 500 -> 2) whose packed image fits
+//     the constant bank: per control period ONE controller launch (controller_cw_kernel: weights fetched into uniform registers,
+//     4 points per thread) and ONE plant launch (rollout_ode_kernel: one trajectory per thread); the state travels through the
+//     X_end / U arrays the call returns anyway -- see the end of this file;
+//   * other narrow controllers: rollout_blocked_kernel, a thread owns 4 trajectories for the whole horizon, weights in shared memory;
+//   * general controllers: rollout_kernel, one trajectory per thread for the whole horizon.
+// The only HBM traffic is the state / disturbance read and the X_end / U write per period.
 #pragma once
 #ifndef __CUDACC_RTC__
 #include "common.cuh"
