@@ -437,13 +437,22 @@ def run_ours(args):
         # the CPU restatement (OpenMP over trajectories) on the host cores next to it -- rank 0, one GPU only
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             ns = min(N, 100000)
-            t0 = time.perf_counter()
-            ctx.rollout(du, "Unicycle", x0[:ns], Wd[:, :ns], 0.0, 0.2, 10.0, iters, post=("shift", -20.0), counts=False)
-            t1 = time.perf_counter()
-            ctx.rollout(du, "Unicycle", x0[:ns], Wd[:, :ns], 0.0, 0.2, 10.0, iters, post=("shift", -20.0), counts=False)
-            t2 = time.perf_counter()
-            line["secondary"]["e2e"] = {"value": ns / min(t1 - t0, t2 - t1), "unit": "trajectories/s", "sample": f"{ns} trajectories",
-                                        "h2d_bytes": int(8 * ns * (4 + iters)), "d2h_bytes": int(8 * ns * iters * 6)}
+            # pinned host buffers (the contract's end-to-end figure); `pageable` = fresh NumPy arrays, what a caller that does not
+            # page-lock its arrays sees (clr_host_register pins them in place)
+            hx = torch.from_numpy(x0[:ns].copy()).pin_memory().numpy()
+            hw = torch.from_numpy(np.ascontiguousarray(Wd[:, :ns])).pin_memory().numpy()
+            hout = {"X_end": torch.empty((iters, ns, 4), dtype=torch.float64).pin_memory().numpy(),
+                    "U": torch.empty((iters, ns, 2), dtype=torch.float64).pin_memory().numpy()}
+            best = {}
+            for tag, kw, xa, wa in (("pinned", {"out": hout}, hx, hw), ("pageable", {}, x0[:ns], Wd[:, :ns])):
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    ctx.rollout(du, "Unicycle", xa, wa, 0.0, 0.2, 10.0, iters, post=("shift", -20.0), counts=False, **kw)
+                    ts.append(time.perf_counter() - t0)
+                best[tag] = ns / min(ts[1:])
+            line["secondary"]["e2e"] = {"value": best["pinned"], "unit": "trajectories/s", "sample": f"{ns} trajectories, pinned host buffers",
+                                        "pageable": best["pageable"], "h2d_bytes": int(8 * ns * (4 + iters)), "d2h_bytes": int(8 * ns * iters * 6)}
             from oracle import cbind
             nc = min(N, 20000)
             on = cbind.Net(uni.as_tuples())

@@ -448,8 +448,9 @@ class Context:
         return U
 
     def rollout(self, dnet: DeviceNetwork, plant, x0, Wd, t0, tau, T, iters, alg="Tsit5", abstol=1e-6, reltol=1e-3,
-                substeps=4, pow_mode=1, pre=None, post=None, log_cap=0, counts=True):
-        """x0: (N, n_state); Wd: (iters, N, n_dist) or None.  Returns X_end (iters, N, n_state), U (iters, N, n_ctrl)."""
+                substeps=4, pow_mode=1, pre=None, post=None, log_cap=0, counts=True, out=None):
+        """x0: (N, n_state); Wd: (iters, N, n_dist) or None.  Returns X_end (iters, N, n_state), U (iters, N, n_ctrl).
+        `out` = {"X_end": array, "U": array}: results go into the caller's (e.g. page-locked, reused) arrays."""
         user = plant if isinstance(plant, CompiledPlant) else None
         pid = 0 if user else (PLANTS[plant] if isinstance(plant, str) else int(plant))
         ns, nd, nc = user.dims if user else PLANT_DIMS.get(pid, (0, 0, 0))
@@ -464,8 +465,11 @@ class Context:
                 raise ClrArgumentError(ERR_ARG, "the plant has disturbances: Wd is required")
             Wd = np.ascontiguousarray(Wd, dtype=np.float64).reshape(iters, N, nd)
         pp = PrePostArg(pre, post)
-        X_end = np.empty((iters, N, ns))
-        U = np.empty((iters, N, nc))
+        X_end = out["X_end"] if out else np.empty((iters, N, ns))
+        U = out["U"] if out else np.empty((iters, N, nc))
+        if X_end.shape != (iters, N, ns) or U.shape != (iters, N, nc) or X_end.dtype != np.float64 or U.dtype != np.float64 \
+                or not X_end.flags.c_contiguous or not U.flags.c_contiguous:
+            raise ClrArgumentError(ERR_DIM, "out arrays must be C-contiguous float64 of shapes (iters, N, n_state) / (iters, N, n_ctrl)")
         na = np.zeros((iters, N), dtype=np.int32) if counts else None
         nr = np.zeros((iters, N), dtype=np.int32) if counts else None
         ln = lt = lu = None
@@ -482,12 +486,12 @@ class Context:
             rc = self.L.clr_rollout(self.h, dnet.h, C.byref(pp.s), pid, x0.shape[1], nd, nc, N, int(iters), _ptr(x0),
                                     _ptr(Wd) if nd else None, *tail)
         self._check(rc)
-        out = {"X_end": X_end, "U": U}
+        res = {"X_end": X_end, "U": U}
         if counts:
-            out.update(naccept=na, nreject=nr)
+            res.update(naccept=na, nreject=nr)
         if log_cap:
-            out.update(log_n=ln, log_t=lt, log_u=lu)
-        return out
+            res.update(log_n=ln, log_t=lt, log_u=lu)
+        return res
 
     def rollout_dev(self, dnet, plant, N, iters, d_x0, d_Wd, t0, tau, T, alg, abstol, reltol, substeps, pow_mode,
                     pp: PrePostArg, d_X_end, d_U, d_naccept=None, d_nreject=None):
